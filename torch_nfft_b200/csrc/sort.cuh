@@ -1,0 +1,347 @@
+// Deterministic binning of non-uniform points by (batch entry, grid tile).
+//
+// Replaces the reference's per-point scratch (compute_shifts_kernel / compute_psi_kernel,
+// csrc/cuda/spatial_window_operations.cu:38-97 -- 4*d*(2m+3) bytes per point written to and
+// re-read from HBM) with a 4-byte key and a 4-byte permutation entry per point.
+//
+// The cell rule is the reference's: cell_a = (int)floorf(pos_a * M)  (:50).  Keys are sorted
+// with a stable LSD radix sort (8-bit digits, per-block digit histograms -> exclusive scan ->
+// in-order scatter), so the permutation is a pure function of the keys: bit-reproducible and
+// equal to numpy's argsort(kind="stable") (tests/test_sort.py).
+#pragma once
+#include "common.cuh"
+
+namespace nfftb200 {
+
+// ------------------------------------------------------------------------- block scan helpers
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one value per thread over the block (blockDim.x <= 1024, multiple of 32).
+// Returns the exclusive prefix; *total receives the block sum.  s_warp: >= 33 uint32.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t incl = warp_incl_scan(v);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? s_warp[lane] : 0u;
+        uint32_t wi = warp_incl_scan(w);
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    uint32_t res = s_warp[warp] + incl - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+// ------------------------------------------------------------------------- device-wide scan
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_reduce_kernel(const uint32_t* __restrict__ in, long long count, uint32_t* __restrict__ partial) {
+    __shared__ uint32_t s_warp[33];
+    const long long base = (long long)blockIdx.x * kScanTile;
+    uint32_t s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        long long i = base + (long long)k * kScanThreads + threadIdx.x;
+        if (i < count) s += in[i];
+    }
+    uint32_t total;
+    block_excl_scan(s, s_warp, &total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of partial[0..nparts), total written to partial[nparts]
+__global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* partial, int nparts) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t running = 0;
+    for (int base = 0; base < nparts; base += 1024) {
+        int i = base + threadIdx.x;
+        uint32_t v = i < nparts ? partial[i] : 0u;
+        uint32_t total;
+        uint32_t ex = block_excl_scan(v, s_warp, &total);
+        if (i < nparts) partial[i] = running + ex;
+        running += total;
+    }
+    if (threadIdx.x == 0) partial[nparts] = running;
+}
+
+// out[i] = exclusive prefix of in; out[count] = total.  in may alias out.
+__global__ void __launch_bounds__(kScanThreads)
+scan_final_kernel(const uint32_t* in, uint32_t* out, long long count, const uint32_t* __restrict__ partial,
+                  int nparts) {
+    __shared__ uint32_t s_warp[33];
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        long long i = base + k;
+        v[k] = i < count ? in[i] : 0u;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_excl_scan(s, s_warp, &total) + partial[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        long long i = base + k;
+        if (i < count) out[i] = ex;
+        ex += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[count] = partial[nparts];
+}
+
+inline size_t scan_scratch_bytes(long long count) {
+    long long nparts = (count + kScanTile - 1) / kScanTile;
+    if (nparts < 1) nparts = 1;
+    return align_up((size_t)(nparts + 1) * sizeof(uint32_t));
+}
+
+// exclusive scan of `count` uint32 (count >= 0); writes count+1 entries to out.
+inline int scan_exclusive(const uint32_t* in, uint32_t* out, long long count, uint32_t* scratch,
+                          cudaStream_t st) {
+    int nparts = (int)((count + kScanTile - 1) / kScanTile);
+    if (nparts < 1) nparts = 1;
+    NF_LAUNCH(scan_reduce_kernel, nparts, kScanThreads, 0, st, in, count, scratch);
+    NF_LAUNCH(scan_partials_kernel, 1, 1024, 0, st, scratch, nparts);
+    NF_LAUNCH(scan_final_kernel, nparts, kScanThreads, 0, st, in, out, count, scratch, nparts);
+    return NFFTB200_OK;
+}
+
+// ------------------------------------------------------------------------- keys + bin counts
+__device__ __forceinline__ int wrap_mod(int v, int M) {
+    v %= M;
+    return v < 0 ? v + M : v;
+}
+
+// key = ((b*nt[2] + tz)*nt[1] + ty)*nt[0] + tx, tile index from the wrapped reference cell.
+__global__ void __launch_bounds__(256)
+key_hist_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, long long n, Geom g,
+                uint32_t* __restrict__ keys, uint32_t* __restrict__ bin_count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long b = batch ? batch[i] : 0;
+    b = b < 0 ? 0 : (b >= g.B ? g.B - 1 : b);
+    uint32_t key = (uint32_t)b;
+    const float Mf = (float)g.M;
+    for (int slot = g.dim - 1; slot >= 0; --slot) {
+        const int a = g.dim - 1 - slot;
+        int c = (int)floorf(pos[i * g.dim + a] * Mf);  // spatial_window_operations.cu:50
+        int cw = wrap_mod(c, g.M);
+        key = key * (uint32_t)g.nt[slot] + (uint32_t)(cw / g.T[slot]);
+    }
+    keys[i] = key;
+    atomicAdd(&bin_count[key], 1u);
+}
+
+// ------------------------------------------------------------------------- stable radix sort
+constexpr int kRsThreads = 256;
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsIpt = 16;  // items per thread
+constexpr int kRsTile = kRsThreads * kRsIpt;
+constexpr int kRsBins = 256;
+
+// table[digit * nblocks + block] = number of keys of `block` whose digit is `digit`
+__global__ void __launch_bounds__(kRsThreads)
+radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ table,
+                  int nblocks) {
+    __shared__ uint32_t hist[kRsBins];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kRsTile;
+    for (int k = 0; k < kRsIpt; ++k) {
+        long long i = base + (long long)k * kRsThreads + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    table[(long long)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// In-order scatter.  Warp w of a block owns the contiguous items [base + w*512, +512) and walks
+// them 32 at a time, so (block, warp, round, lane) order == input order and equal digits keep
+// their relative order (stable).  idx_in == nullptr means the identity payload.
+__global__ void __launch_bounds__(kRsThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, long long n, int shift,
+                     const uint32_t* __restrict__ table_scanned, int nblocks) {
+    __shared__ uint32_t wcnt[kRsWarps][kRsBins];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < kRsWarps * kRsBins; k += kRsThreads) (&wcnt[0][0])[k] = 0;
+    __syncthreads();
+
+    const long long base = (long long)blockIdx.x * kRsTile + (long long)warp * (32 * kRsIpt);
+    uint32_t key[kRsIpt];
+    uint32_t rank[kRsIpt];
+#pragma unroll
+    for (int s = 0; s < kRsIpt; ++s) {
+        const long long i = base + s * 32 + lane;
+        const bool valid = i < n;
+        key[s] = valid ? keys_in[i] : 0xffffffffu;
+        const uint32_t digit = valid ? ((key[s] >> shift) & 255u) : 256u;
+        const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(mask) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = wcnt[warp][digit];
+            wcnt[warp][digit] = old + __popc(mask);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[s] = old + __popc(mask & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // exclusive prefix over the warps of this block, seeded with the global offset
+        const int d = threadIdx.x;
+        uint32_t running = table_scanned[(long long)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kRsWarps; ++w) {
+            uint32_t t = wcnt[w][d];
+            wcnt[w][d] = running;
+            running += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < kRsIpt; ++s) {
+        const long long i = base + s * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (key[s] >> shift) & 255u;
+            const uint32_t dst = wcnt[warp][digit] + rank[s];
+            keys_out[dst] = key[s];
+            idx_out[dst] = idx_in ? idx_in[i] : (uint32_t)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+// ------------------------------------------------------------------------- work items
+// number of chunks per bin: ceil(count / pmax)
+__global__ void __launch_bounds__(256)
+chunk_count_kernel(const uint32_t* __restrict__ bin_start, long long nbins, int pmax, uint32_t* __restrict__ nch) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    uint32_t c = bin_start[b + 1] - bin_start[b];
+    nch[b] = (c + (uint32_t)pmax - 1u) / (uint32_t)pmax;
+}
+
+__global__ void __launch_bounds__(256)
+fill_items_kernel(const uint32_t* __restrict__ chunk_start, long long nbins, int2* __restrict__ items) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    const uint32_t lo = chunk_start[b], hi = chunk_start[b + 1];
+    for (uint32_t w = lo; w < hi; ++w) items[w] = make_int2((int)b, (int)(w - lo));
+}
+
+// ------------------------------------------------------------------------- host orchestration
+struct SortLayout {
+    size_t keys0, keysA, keysB, idxA, idxB, bin_count, bin_start, nch, chunk_start, items, table, scan, total;
+    long long nbins, max_items, nblocks;
+};
+
+inline SortLayout sort_layout(long long n, const Geom& g) {
+    SortLayout L{};
+    L.nbins = (long long)g.B * g.tiles_per_batch;
+    L.nblocks = (n + kRsTile - 1) / kRsTile;
+    if (L.nblocks < 1) L.nblocks = 1;
+    L.max_items = n / g.pmax + (L.nbins < n ? L.nbins : n) + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes);
+        return o;
+    };
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    L.keys0 = take(nn * 4);
+    L.keysA = take(nn * 4);
+    L.keysB = take(nn * 4);
+    L.idxA = take(nn * 4);
+    L.idxB = take(nn * 4);
+    L.bin_count = take((size_t)(L.nbins + 1) * 4);
+    L.bin_start = take((size_t)(L.nbins + 1) * 4);
+    L.nch = take((size_t)(L.nbins + 1) * 4);
+    L.chunk_start = take((size_t)(L.nbins + 1) * 4);
+    L.items = take((size_t)L.max_items * sizeof(int2));
+    L.table = take((size_t)(kRsBins * L.nblocks + 1) * 4);
+    size_t s1 = scan_scratch_bytes(L.nbins + 1);
+    size_t s2 = scan_scratch_bytes(kRsBins * L.nblocks + 1);
+    L.scan = take(s1 > s2 ? s1 : s2);
+    L.total = off;
+    return L;
+}
+
+// Bins n points; on return plan.* point into `ws` (which must hold sort_layout(n,g).total bytes).
+inline int sort_points(const float* pos, const int64_t* batch, long long n, const Geom& g, char* ws,
+                       SortPlan* plan, cudaStream_t st) {
+    const SortLayout L = sort_layout(n, g);
+    uint32_t* keys0 = (uint32_t*)(ws + L.keys0);
+    uint32_t* kbuf[2] = {(uint32_t*)(ws + L.keysA), (uint32_t*)(ws + L.keysB)};
+    uint32_t* ibuf[2] = {(uint32_t*)(ws + L.idxA), (uint32_t*)(ws + L.idxB)};
+    uint32_t* bin_count = (uint32_t*)(ws + L.bin_count);
+    uint32_t* bin_start = (uint32_t*)(ws + L.bin_start);
+    uint32_t* nch = (uint32_t*)(ws + L.nch);
+    uint32_t* chunk_start = (uint32_t*)(ws + L.chunk_start);
+    uint32_t* table = (uint32_t*)(ws + L.table);
+    uint32_t* scan = (uint32_t*)(ws + L.scan);
+
+    NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(L.nbins + 1) * 4, st));
+    if (n > 0) {
+        NF_LAUNCH(key_hist_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pos, batch, n, g, keys0, bin_count);
+    }
+    NF_TRY(scan_exclusive(bin_count, bin_start, L.nbins, scan, st));
+    NF_LAUNCH(chunk_count_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, bin_start, L.nbins, g.pmax, nch);
+    NF_TRY(scan_exclusive(nch, chunk_start, L.nbins, scan, st));
+    NF_LAUNCH(fill_items_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, chunk_start, L.nbins,
+              (int2*)(ws + L.items));
+
+    // stable LSD radix sort of (key, index) over the key bits that can be set
+    int bits = 0;
+    while (bits < 32 && (1ll << bits) < L.nbins) ++bits;
+    const int passes = (bits + 7) / 8;
+    const uint32_t* kin = keys0;
+    const uint32_t* iin = nullptr;  // identity payload on the first pass
+    uint32_t* perm = ibuf[0];
+    if (n > 0) {
+        if (passes == 0) {
+            NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, ibuf[0], n);
+        }
+        for (int p = 0; p < passes; ++p) {
+            uint32_t* kout = kbuf[p & 1];
+            uint32_t* iout = ibuf[p & 1];
+            NF_LAUNCH(radix_hist_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, n, 8 * p, table,
+                      (int)L.nblocks);
+            NF_TRY(scan_exclusive(table, table, kRsBins * L.nblocks, scan, st));
+            NF_LAUNCH(radix_scatter_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, iin, kout, iout, n, 8 * p,
+                      table, (int)L.nblocks);
+            kin = kout;
+            iin = iout;
+            perm = iout;
+        }
+    }
+    plan->keys = keys0;
+    plan->perm = perm;
+    plan->bin_start = bin_start;
+    plan->chunk_start = chunk_start;
+    plan->items = (int2*)(ws + L.items);
+    plan->nbins = L.nbins;
+    plan->max_items = L.max_items;
+    return NFFTB200_OK;
+}
+
+}  // namespace nfftb200

@@ -1,0 +1,411 @@
+// Spatial window kernels: adjoint spreading and forward interpolation on shared-memory tiles.
+//
+// Replaces real_/complex_adjoint_window_convolution_kernel and real_/complex_forward_window_
+// convolution_kernel (reference csrc/cuda/spatial_window_operations.cu:103-332), which issue one
+// global float atomic per (point, channel, tap).  Here every work item = (grid tile, chunk of the
+// tile's sorted points) owns a zero-initialised shared-memory copy of the padded tile:
+//
+//  * spread: the CTA is a "team" in which every thread owns a residue class of tile cells
+//    (3D: (y mod L, z mod L), 2D: (x mod L, y mod L), 1D: x mod L).  A point's (2m+2)^d stencil
+//    contains exactly one row / cell of every class, so all threads walk the same point list and
+//    each accumulates its own cells with plain LDS/FFMA/STS -- no shared-memory float atomics
+//    (a CAS loop on sm_100a) and a fixed accumulation order inside the tile.  The tile is then
+//    flushed to HBM with 16-byte vector reductions (RED.E.ADD.F32x4), skipping untouched cells.
+//  * gather: the padded tile is staged into shared memory with 16-byte loads, one warp per
+//    point, lanes over stencil rows, warp-shuffle reduction, one plain store per point/channel
+//    (no atomics on y, unlike spatial_window_operations.cu:267,317).
+//
+// Window taps are recomputed in registers/shared memory from pos (never stored to HBM):
+//   shift = (int)floorf(pos*M) - m,  psi_l = expf(-t*t*inv_b)*s,  t = (float)((double)pos*M - shift - l)
+// exactly as spatial_window_operations.cu:50,84-86,24-28 (the argument is formed in double there).
+#pragma once
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace nfftb200 {
+
+struct WindowArgs {
+    const float* pos;        // [n, dim]
+    const float* xin;        // spread: values [n, K] (float components)
+    float* yout;             // gather: values [n, K]
+    float* grid;             // planar grid, see grid_addr()
+    const uint32_t* perm;
+    const uint32_t* bin_start;
+    const uint32_t* chunk_start;
+    const int2* items;
+    long long nbins;
+    int k0;                  // first component handled by this pass
+};
+
+__device__ __forceinline__ int fast_div(int x, int d, float inv) {
+    int q = (int)((float)x * inv);
+    if (q * d > x) --q;
+    if ((q + 1) * d <= x) ++q;
+    return q;
+}
+
+// Stage `cnt` points (sorted positions p0..p0+cnt) into shared memory:
+//   s_psi[(q*DIM + slot)*LP + l], s_rec[q*8 + {0,1,2}] = first-tap coordinate in the padded tile,
+//   s_rec[q*8 + 3] = original point index, s_rec[q*8 + 4 + slot] = first-tap coordinate mod L.
+template <int DIM>
+__device__ __forceinline__ void stage_points(const Geom& g, const WindowArgs& a, long long p0, int cnt,
+                                             const int* tile_org, float* s_psi, int* s_rec) {
+    const int L = g.L, LP = g.LP;
+    for (int w = threadIdx.x; w < cnt * DIM; w += blockDim.x) {
+        const int q = w / DIM, slot = w - q * DIM;
+        const int api = DIM - 1 - slot;
+        const uint32_t i = a.perm[p0 + q];
+        const float p = a.pos[(size_t)i * DIM + api];
+        const int c = (int)floorf(p * (float)g.M);  // reference cell (spatial_window_operations.cu:50)
+        const int sh = c - g.m;                      // reference shift
+        const double base = (double)p * (double)g.M - (double)sh;
+        float* ps = s_psi + (q * DIM + slot) * LP;
+        for (int l = 0; l < L; ++l) {
+            const float t = (float)(base - (double)l);
+            ps[l] = expf(-(t * t) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+        }
+        for (int l = L; l < LP; ++l) ps[l] = 0.f;
+        // first tap in padded-tile coordinates: wrapped cell - m - (tile origin)
+        int s0 = wrap_mod(c, g.M) - g.m - tile_org[slot];
+        s_rec[q * 8 + slot] = s0;
+        s_rec[q * 8 + 4 + slot] = s0 % L;
+        if (slot == 0) {
+            s_rec[q * 8 + 3] = (int)i;
+            if (DIM < 3) { s_rec[q * 8 + 2] = 0; s_rec[q * 8 + 6] = 0; }
+            if (DIM < 2) { s_rec[q * 8 + 1] = 0; s_rec[q * 8 + 5] = 0; }
+            s_rec[q * 8 + 7] = 0;
+        }
+    }
+}
+
+// address (in floats) of component k of grid cell `cell` for batch entry b
+__device__ __forceinline__ size_t grid_plane(const Geom& g, int b, int k) {
+    // real: plane (b*C + k); complex: plane (b*C + k/2), interleaved re/im
+    return g.cplx ? (size_t)((long long)b * g.C + (k >> 1)) * (size_t)g.Md * 2 : (size_t)((long long)b * g.C + k) * (size_t)g.Md;
+}
+
+struct TileCtx {
+    int b, org[3];
+    long long p_lo, p_hi;
+};
+
+__device__ __forceinline__ bool decode_item(const Geom& g, const WindowArgs& a, TileCtx& t) {
+    const uint32_t total = a.chunk_start[a.nbins];
+    if (blockIdx.x >= total) return false;
+    const int2 it = a.items[blockIdx.x];
+    const int bin = it.x;
+    const uint32_t lo = a.bin_start[bin], hi = a.bin_start[bin + 1];
+    const uint32_t nch = a.chunk_start[bin + 1] - a.chunk_start[bin];
+    const unsigned long long cnt = hi - lo;
+    t.p_lo = lo + (long long)(cnt * (unsigned long long)it.y / nch);
+    t.p_hi = lo + (long long)(cnt * (unsigned long long)(it.y + 1) / nch);
+    t.b = bin / g.tiles_per_batch;
+    int r = bin - t.b * g.tiles_per_batch;
+    const int tx = r % g.nt[0];
+    r /= g.nt[0];
+    const int ty = r % g.nt[1];
+    const int tz = r / g.nt[1];
+    t.org[0] = tx * g.T[0] - g.org[0];
+    t.org[1] = ty * g.T[1] - g.org[1];
+    t.org[2] = tz * g.T[2] - g.org[2];
+    return true;
+}
+
+// iterate over the padded tile in groups of 4 consecutive X cells; f(smem_offset, global_cell)
+template <int DIM, typename F>
+__device__ __forceinline__ void for_each_quad(const Geom& g, const TileCtx& t, F f) {
+    const int nx4 = g.P[0] >> 2;
+    const int rows = (DIM >= 2 ? g.P[1] : 1) * (DIM >= 3 ? g.P[2] : 1);
+    const int total = rows * nx4;
+    const float inv_nx4 = 1.0f / (float)nx4;
+    const float inv_p1 = 1.0f / (float)g.P[1];
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int row = fast_div(idx, nx4, inv_nx4);
+        const int x = (idx - row * nx4) << 2;
+        int y = 0, z = 0;
+        if (DIM >= 3) {
+            z = fast_div(row, g.P[1], inv_p1);
+            y = row - z * g.P[1];
+        } else if (DIM == 2) {
+            y = row;
+        }
+        const int gx = wrap_mod(t.org[0] + x, g.M);
+        long long cell = gx;
+        int so = x;
+        if (DIM >= 2) {
+            cell += (long long)wrap_mod(t.org[1] + y, g.M) * g.M;
+            so += y * g.sY;
+        }
+        if (DIM >= 3) {
+            cell += (long long)wrap_mod(t.org[2] + z, g.M) * g.M * g.M;
+            so += z * g.sZ;
+        }
+        f(so, cell);
+    }
+}
+
+// ======================================================================================
+// adjoint spreading
+// ======================================================================================
+template <int DIM, int NCOMP, int LC>
+__global__ void __launch_bounds__(384)
+spread_kernel(const Geom g, const WindowArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+
+    const int L = LC ? LC : g.L;
+    const int LP = g.LP;
+    float* tile = smem;
+    float* s_psi = tile + (size_t)NCOMP * g.tile_elems;
+    float* s_xv = s_psi + kSubBatch * DIM * LP;
+    int* s_rec = (int*)(s_xv + kSubBatch * NCOMP);
+    __shared__ int s_org[3];
+    if (threadIdx.x < 3) s_org[threadIdx.x] = t.org[threadIdx.x];
+
+    for (int i = threadIdx.x; i < NCOMP * g.tile_elems; i += blockDim.x) tile[i] = 0.f;
+
+    // residue classes owned by this thread
+    const int tid = threadIdx.x;
+    int c0, c1;  // DIM3: (y class, z class); DIM2: (x class, y class); DIM1: x class
+    bool active;
+    if (DIM == 1) {
+        c0 = tid; c1 = 0; active = tid < L;
+    } else {
+        c1 = tid / L; c0 = tid - c1 * L; active = tid < L * L;
+    }
+    __syncthreads();
+
+    for (long long p0 = t.p_lo; p0 < t.p_hi; p0 += kSubBatch) {
+        const int cnt = (int)((t.p_hi - p0) < kSubBatch ? (t.p_hi - p0) : kSubBatch);
+        stage_points<DIM>(g, a, p0, cnt, s_org, s_psi, s_rec);
+        for (int w = tid; w < cnt * NCOMP; w += blockDim.x) {
+            const int q = w / NCOMP, k = w - q * NCOMP;
+            const uint32_t i = a.perm[p0 + q];
+            s_xv[w] = (a.k0 + k < g.K) ? a.xin[(size_t)i * g.K + a.k0 + k] : 0.f;
+        }
+        __syncthreads();
+        if (active) {
+            for (int q = 0; q < cnt; ++q) {
+                const int4 st = *reinterpret_cast<const int4*>(s_rec + q * 8);
+                const int4 md = *reinterpret_cast<const int4*>(s_rec + q * 8 + 4);
+                const float* ps = s_psi + q * DIM * LP;
+                float v[NCOMP];
+#pragma unroll
+                for (int k = 0; k < NCOMP; ++k) v[k] = s_xv[q * NCOMP + k];
+                if (DIM == 3) {
+                    int ay = c0 - md.y; ay += ay < 0 ? L : 0;
+                    int az = c1 - md.z; az += az < 0 ? L : 0;
+                    const float wz = ps[2 * LP + az], wy = ps[LP + ay];
+                    // reference product order: x * psi(dim 0 = Z) * psi(dim 1 = Y) * psi(dim 2 = X)
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) v[k] = (v[k] * wz) * wy;
+                    float* row = tile + (st.z + az) * g.sZ + (st.y + ay) * g.sY + st.x;
+                    if (LC) {
+                        float wx[LC ? LC : 1];
+#pragma unroll
+                        for (int l = 0; l < LC; ++l) wx[l] = ps[l];
+#pragma unroll
+                        for (int k = 0; k < NCOMP; ++k) {
+                            float* r = row + (size_t)k * g.tile_elems;
+                            float acc[LC ? LC : 1];
+#pragma unroll
+                            for (int l = 0; l < LC; ++l) acc[l] = r[l];
+#pragma unroll
+                            for (int l = 0; l < LC; ++l) acc[l] = fmaf(v[k], wx[l], acc[l]);
+#pragma unroll
+                            for (int l = 0; l < LC; ++l) r[l] = acc[l];
+                        }
+                    } else {
+                        for (int l = 0; l < L; ++l) {
+                            const float wx = ps[l];
+#pragma unroll
+                            for (int k = 0; k < NCOMP; ++k) {
+                                float* r = row + (size_t)k * g.tile_elems + l;
+                                *r = fmaf(v[k], wx, *r);
+                            }
+                        }
+                    }
+                } else if (DIM == 2) {
+                    int ax = c0 - md.x; ax += ax < 0 ? L : 0;
+                    int ay = c1 - md.y; ay += ay < 0 ? L : 0;
+                    const float wy = ps[LP + ay], wx = ps[ax];
+                    float* cellp = tile + (st.y + ay) * g.sY + st.x + ax;
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) {
+                        float* r = cellp + (size_t)k * g.tile_elems;
+                        *r = fmaf(v[k] * wy, wx, *r);
+                    }
+                } else {
+                    int ax = c0 - md.x; ax += ax < 0 ? L : 0;
+                    const float wx = ps[ax];
+                    float* cellp = tile + st.x + ax;
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) {
+                        float* r = cellp + (size_t)k * g.tile_elems;
+                        *r = fmaf(v[k], wx, *r);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // flush: vector reductions into the global grid; untouched (== 0) quads are skipped
+    if (!g.cplx) {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) {
+                if (a.k0 + k < g.K) {
+                    const float* s = tile + (size_t)k * g.tile_elems + so;
+                    const float4 val = make_float4(s[0], s[1], s[2], s[3]);
+                    if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) {
+                        float4* dst = reinterpret_cast<float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell);
+                        atomicAdd(dst, val);
+                    }
+                }
+            }
+        });
+    } else {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k + 1 < NCOMP; k += 2) {
+                if (a.k0 + k < g.K) {
+                    const float* re = tile + (size_t)k * g.tile_elems + so;
+                    const float* im = tile + (size_t)(k + 1) * g.tile_elems + so;
+                    float* dst = a.grid + grid_plane(g, t.b, a.k0 + k) + 2 * cell;
+                    const float4 v0 = make_float4(re[0], im[0], re[1], im[1]);
+                    const float4 v1 = make_float4(re[2], im[2], re[3], im[3]);
+                    if (v0.x != 0.f || v0.y != 0.f || v0.z != 0.f || v0.w != 0.f)
+                        atomicAdd(reinterpret_cast<float4*>(dst), v0);
+                    if (v1.x != 0.f || v1.y != 0.f || v1.z != 0.f || v1.w != 0.f)
+                        atomicAdd(reinterpret_cast<float4*>(dst + 4), v1);
+                }
+            }
+        });
+    }
+}
+
+// ======================================================================================
+// forward interpolation
+// ======================================================================================
+constexpr int kGatherThreads = 256;
+
+template <int DIM, int NCOMP, int LC>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(const Geom g, const WindowArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+
+    const int L = LC ? LC : g.L;
+    const int LP = g.LP;
+    float* tile = smem;
+    float* s_psi = tile + (size_t)NCOMP * g.tile_elems;
+    int* s_rec = (int*)(s_psi + kSubBatch * DIM * LP);
+    __shared__ int s_org[3];
+    if (threadIdx.x < 3) s_org[threadIdx.x] = t.org[threadIdx.x];
+
+    // stage the padded tile (periodic wrap resolved per quad)
+    if (!g.cplx) {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) {
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.k0 + k < g.K)
+                    val = __ldg(reinterpret_cast<const float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell));
+                float* s = tile + (size_t)k * g.tile_elems + so;
+                s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
+            }
+        });
+    } else {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k < NCOMP; k += 2) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (a.k0 + k < g.K) {
+                    const float* src = a.grid + grid_plane(g, t.b, a.k0 + k) + 2 * cell;
+                    v0 = __ldg(reinterpret_cast<const float4*>(src));
+                    v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                }
+                float* re = tile + (size_t)k * g.tile_elems + so;
+                float* im = tile + (size_t)(k + 1 < NCOMP ? k + 1 : k) * g.tile_elems + so;
+                re[0] = v0.x; re[1] = v0.z; re[2] = v1.x; re[3] = v1.z;
+                if (k + 1 < NCOMP) { im[0] = v0.y; im[1] = v0.w; im[2] = v1.y; im[3] = v1.w; }
+            }
+        });
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (long long p0 = t.p_lo; p0 < t.p_hi; p0 += kSubBatch) {
+        const int cnt = (int)((t.p_hi - p0) < kSubBatch ? (t.p_hi - p0) : kSubBatch);
+        stage_points<DIM>(g, a, p0, cnt, s_org, s_psi, s_rec);
+        __syncthreads();
+        for (int q = warp; q < cnt; q += nwarps) {
+            const int4 st = *reinterpret_cast<const int4*>(s_rec + q * 8);
+            const float* ps = s_psi + q * DIM * LP;
+            float acc[NCOMP];
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) acc[k] = 0.f;
+            if (DIM == 3) {
+                const float* base = tile + st.z * g.sZ + st.y * g.sY + st.x;
+                float wx[LC ? LC : 1];
+                if (LC) {
+#pragma unroll
+                    for (int l = 0; l < LC; ++l) wx[l] = ps[l];
+                }
+                int ay = lane % L, az = lane / L;
+                for (int r = lane; r < L * L; r += 32) {
+                    const float w = ps[2 * LP + az] * ps[LP + ay];  // psi(Z) * psi(Y), then * psi(X)
+                    const float* row = base + az * g.sZ + ay * g.sY;
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) {
+                        const float* rk = row + (size_t)k * g.tile_elems;
+                        float inner = 0.f;
+                        if (LC) {
+#pragma unroll
+                            for (int l = 0; l < LC; ++l) inner = fmaf(w * wx[l], rk[l], inner);
+                        } else {
+                            for (int l = 0; l < L; ++l) inner = fmaf(w * ps[l], rk[l], inner);
+                        }
+                        acc[k] += inner;
+                    }
+                    ay += 32;
+                    while (ay >= L) { ay -= L; ++az; }
+                }
+            } else if (DIM == 2) {
+                const float* base = tile + st.y * g.sY + st.x;
+                int ax = lane % L, ay = lane / L;
+                for (int r = lane; r < L * L; r += 32) {
+                    const float w = ps[LP + ay] * ps[ax];
+                    const float* cellp = base + ay * g.sY + ax;
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) acc[k] = fmaf(w, cellp[(size_t)k * g.tile_elems], acc[k]);
+                    ax += 32;
+                    while (ax >= L) { ax -= L; ++ay; }
+                }
+            } else {
+                if (lane < L) {
+                    const float w = ps[lane];
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) acc[k] = w * tile[(size_t)k * g.tile_elems + st.x + lane];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+            if (lane == 0) {
+                float* dst = a.yout + (size_t)(uint32_t)st.w * g.K + a.k0;
+#pragma unroll
+                for (int k = 0; k < NCOMP; ++k)
+                    if (a.k0 + k < g.K) dst[k] = acc[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace nfftb200
