@@ -1,0 +1,354 @@
+"""GPU parity tests: the sm_100a engine (through the C ABI) against the numpy oracle on seeded
+inputs, against the golden fixtures produced by the compiled reference, and -- at the full
+BASELINE sizes -- through size-independent properties.
+
+Tolerance: relative L2 <= 1e-5 in fp32 (BASELINE.json north_star).  Integer work (tile keys,
+sort permutation) must be bit-exact.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, golden_files
+from oracle import nfft_oracle as O
+import torch_nfft_b200 as T
+from torch_nfft_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north-star parity tolerance, relative L2, fp32
+DEV = "cuda"
+
+
+def cuda(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def make_points(rng, d, B, n, ragged=False):
+    if ragged:
+        sizes = rng.integers(0, 2 * n, size=B)
+        sizes[B // 2] = 0  # an empty point set in the middle
+        sizes[-1] = max(sizes[-1], 1)  # batch[-1] must be B-1 (reference README.md:44-46)
+    else:
+        sizes = np.full(B, n)
+    batch = np.repeat(np.arange(B, dtype=np.int64), sizes)
+    pos = rng.random((batch.size, d), dtype=np.float32) - 0.5
+    return pos, batch
+
+
+def make_values(rng, shape, cplx):
+    v = rng.standard_normal(shape).astype(np.float32)
+    if cplx:
+        v = (v + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    return v
+
+
+CASES = [
+    # d, N, m, B, n, C
+    (1, 64, 4, 2, 500, 2),
+    (1, 256, 8, 3, 2000, 1),
+    (2, 32, 4, 3, 700, 3),
+    (2, 64, 3, 2, 1500, 8),
+    (2, 16, 2, 1, 300, 10),
+    (3, 16, 3, 2, 600, 1),
+    (3, 32, 4, 2, 2500, 1),
+    (3, 16, 2, 1, 500, 3),
+    (3, 12, 3, 1, 400, 2),   # bandwidth not a power of two
+    (2, 4, 1, 2, 50, 1),     # smallest legal grid: N = 4, m = 1
+]
+
+
+@pytest.mark.parametrize("d,N,m,B,n,C", CASES)
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("real_output", [False, True])
+def test_adjoint_matches_oracle(d, N, m, B, n, C, cplx, real_output):
+    rng = np.random.default_rng(hash((d, N, m, C, cplx)) % 2 ** 31)
+    pos, batch = make_points(rng, d, B, n)
+    x = make_values(rng, (pos.shape[0], C), cplx)
+    y = T.nfft_adjoint(cuda(x), cuda(pos), cuda(batch), N, m, real_output=real_output)
+    ref = O.nfft_adjoint(x, pos, batch, N, m, real_output=real_output)
+    assert y.shape == ref.shape and y.cpu().numpy().dtype == ref.dtype
+    assert O.rel_l2(y.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("d,N,m,B,n,C", CASES)
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("real_output", [False, True])
+def test_forward_matches_oracle(d, N, m, B, n, C, cplx, real_output):
+    rng = np.random.default_rng(hash((d, N, m, C, cplx, 1)) % 2 ** 31)
+    pos, batch = make_points(rng, d, B, n)
+    xh = make_values(rng, (B,) + (N,) * d + (C,), cplx)
+    y = T.nfft_forward(cuda(xh), cuda(pos), cuda(batch), m, real_output=real_output)
+    ref = O.nfft_forward(xh, pos, batch, m, real_output=real_output)
+    assert y.shape == ref.shape and y.cpu().numpy().dtype == ref.dtype
+    assert O.rel_l2(y.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("d,N,m,B,n,C", [(1, 64, 4, 2, 400, 2), (2, 32, 4, 2, 600, 3), (3, 16, 3, 2, 500, 1), (3, 32, 4, 1, 1500, 2)])
+@pytest.mark.parametrize("xc,cc", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_fastsum_matches_oracle(d, N, m, B, n, C, xc, cc, symmetric):
+    rng = np.random.default_rng(hash((d, N, m, C, xc, cc)) % 2 ** 31)
+    src, sb = make_points(rng, d, B, n)
+    src = (src * 0.5).astype(np.float32)
+    x = make_values(rng, (src.shape[0], C), xc)
+    co = O.gaussian_interpolated_coeffs(0.15, d, N) if cc else O.gaussian_analytic_coeffs(0.15, d, N)
+    if cc:
+        co = (co * np.exp(0.3j)).astype(np.complex64)  # deliberately not Hermitian-even
+    if symmetric:
+        y = T.nfft_fastsum(cuda(x), cuda(co), cuda(src), batch=cuda(sb), cutoff=m)
+        ref = O.nfft_fastsum(x, co, src, None, sb, sb, m=m)
+    else:
+        tgt, tb = make_points(rng, d, B, n // 2 + 1)
+        tgt = (tgt * 0.5).astype(np.float32)
+        y = T.nfft_fastsum(cuda(x), cuda(co), cuda(src), cuda(tgt), cuda(sb), cuda(tb), cutoff=m)
+        ref = O.nfft_fastsum(x, co, src, tgt, sb, tb, m=m)
+    assert y.shape == ref.shape and y.cpu().numpy().dtype == ref.dtype
+    assert O.rel_l2(y.cpu().numpy(), ref) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors of the compiled reference
+# ---------------------------------------------------------------------------------------------
+def _opt(z, k):
+    return cuda(z[k]) if k in z.files else None
+
+
+@pytest.mark.parametrize("fname", golden_files("adjoint") + golden_files("forward") + golden_files("fastsum"))
+def test_engine_matches_reference_golden(fname):
+    z = np.load(os.path.join(GOLDEN_DIR, fname))
+    op = str(z["op"])
+    if op == "adjoint":
+        y = T.nfft_adjoint(cuda(z["x"]), cuda(z["pos"]), _opt(z, "batch"), int(z["N"]), int(z["m"]), bool(z["real_output"]))
+    elif op == "forward":
+        y = T.nfft_forward(cuda(z["x"]), cuda(z["pos"]), _opt(z, "batch"), int(z["m"]), bool(z["real_output"]))
+    else:
+        y = T.nfft_fastsum(cuda(z["x"]), cuda(z["coeffs"]), cuda(z["sources"]), batch=_opt(z, "source_batch"), cutoff=int(z["m"]))
+    assert tuple(y.shape) == z["y"].shape
+    assert O.rel_l2(y.cpu().numpy(), z["y"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# integer work: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,N,m,B,n", [(1, 1024, 8, 5, 3000), (2, 256, 4, 3, 20000), (3, 128, 4, 2, 150000), (3, 16, 3, 2, 999), (2, 64, 3, 300, 50)])
+def test_binning_is_bit_exact(d, N, m, B, n):
+    rng = np.random.default_rng(d + N)
+    pos, batch = make_points(rng, d, B, n, ragged=True)
+    pos[::7] += 1.0  # some points outside [-1/2, 1/2): wrapped cell
+    nn = pos.shape[0]
+    L = _lib.lib()
+    keys = torch.zeros(nn, dtype=torch.int32, device=DEV)
+    perm = torch.zeros(nn, dtype=torch.int32, device=DEV)
+    tile = (ctypes.c_int32 * 3)()
+    nb = L.nfftb200_workspace_bytes(_lib.OP_SORT, nn, 0, d, N, m, B, 1, 0)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    tp, tb = cuda(pos), cuda(batch)
+    for _ in range(2):  # twice: the permutation must be reproducible
+        _lib.check(L.nfftb200_sort_points(tp.data_ptr(), tb.data_ptr(), keys.data_ptr(), perm.data_ptr(),
+                                          ctypes.cast(tile, ctypes.c_void_p), nn, d, N, m, B, 1, 0, ws.data_ptr(),
+                                          ws.numel(), torch.cuda.current_stream().cuda_stream), "sort")
+        torch.cuda.synchronize()
+        okeys = O.tile_keys(pos, batch, N, list(tile)[:d][::-1])
+        assert np.array_equal(keys.cpu().numpy().astype(np.int64), okeys)
+        assert np.array_equal(perm.cpu().numpy().astype(np.int64), O.stable_permutation(okeys))
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def test_empty_and_ragged_inputs():
+    rng = np.random.default_rng(3)
+    # no points at all: adjoint is zero, forward is empty
+    y = T.nfft_adjoint(torch.zeros(0, 2, device=DEV), torch.zeros(0, 2, device=DEV), None, 16, 3)
+    assert y.shape == (1, 16, 16, 2) and float(y.abs().max()) == 0.0
+    f = T.nfft_forward(torch.zeros(1, 16, 16, dtype=torch.complex64, device=DEV), torch.zeros(0, 2, device=DEV), None, 3)
+    assert f.shape == (0,)
+    # ragged batch with an empty point set
+    pos, batch = make_points(rng, 2, 5, 300, ragged=True)
+    x = make_values(rng, (pos.shape[0], 2), False)
+    y = T.nfft_adjoint(cuda(x), cuda(pos), cuda(batch), 16, 4)
+    ref = O.nfft_adjoint(x, pos, batch, 16, 4)
+    assert O.rel_l2(y.cpu().numpy(), ref) < TOL
+    assert float(y[2].abs().max()) == 0.0  # the empty set
+    yf = T.nfft_forward(y, cuda(pos), cuda(batch), 4)
+    assert O.rel_l2(yf.cpu().numpy(), O.nfft_forward(ref, pos, batch, 4)) < TOL
+
+
+def test_one_dimensional_x_and_no_batch():
+    rng = np.random.default_rng(4)
+    pos = rng.random((400, 3), dtype=np.float32) - 0.5
+    x = make_values(rng, (400,), False)
+    y = T.nfft_adjoint(cuda(x), cuda(pos), None, 16, 3)
+    assert y.shape == (1, 16, 16, 16)
+    assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(x, pos, None, 16, 3)) < TOL
+    f = T.nfft_forward(y, cuda(pos), None, 3, real_output=True)
+    assert f.shape == (400,)
+    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(y.cpu().numpy(), pos, None, 3, real_output=True)) < TOL
+    # multi-dimensional channel shape [n, 2, 3]
+    x3 = make_values(rng, (400, 2, 3), True)
+    y3 = T.nfft_adjoint(cuda(x3), cuda(pos), None, 8, 2)
+    assert y3.shape == (1, 8, 8, 8, 2, 3)
+    assert O.rel_l2(y3.cpu().numpy(), O.nfft_adjoint(x3, pos, None, 8, 2)) < TOL
+
+
+def test_periodic_wrap_and_boundary_points():
+    rng = np.random.default_rng(5)
+    pos = rng.random((600, 2), dtype=np.float32) - 0.5
+    pos[0] = [-0.5, -0.5]
+    pos[1] = [np.nextafter(np.float32(0.5), np.float32(0)), 0.0]
+    pos[2] = [0.0, -0.5]
+    x = make_values(rng, (600, 1), False)
+    y = T.nfft_adjoint(cuda(x), cuda(pos), None, 32, 4)
+    assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(x, pos, None, 32, 4)) < TOL
+    moved = pos.copy()
+    moved[:100] += 1.0
+    moved[100:150] -= 1.0
+    y2 = T.nfft_adjoint(cuda(x), cuda(moved), None, 32, 4)
+    assert O.rel_l2(y2.cpu().numpy(), y.cpu().numpy()) < TOL
+    f2 = T.nfft_forward(y, cuda(moved), None, 4)
+    assert O.rel_l2(f2.cpu().numpy(), T.nfft_forward(y, cuda(pos), None, 4).cpu().numpy()) < TOL
+
+
+def test_all_points_in_one_cell():
+    """Maximal collision: every point in the same oversampled cell (one tile, many chunks)."""
+    rng = np.random.default_rng(6)
+    n = 20000
+    pos = (0.123 + 1e-4 * rng.random((n, 3))).astype(np.float32)
+    x = make_values(rng, (n, 1), False)
+    y = T.nfft_adjoint(cuda(x), cuda(pos), None, 16, 3)
+    assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(x, pos, None, 16, 3)) < TOL
+    f = T.nfft_forward(y, cuda(pos), None, 3)
+    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(y.cpu().numpy(), pos, None, 3)) < TOL
+
+
+def test_non_contiguous_inputs_and_side_stream():
+    rng = np.random.default_rng(7)
+    pos = rng.random((500, 2), dtype=np.float32) - 0.5
+    x = make_values(rng, (500, 4), False)
+    tp = cuda(np.concatenate([pos, pos], axis=1))[:, :2]  # strided view
+    tx = cuda(np.concatenate([x, x], axis=1))[:, ::2][:, :2]
+    assert not tp.is_contiguous() and not tx.is_contiguous()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        y = T.nfft_adjoint(tx, tp, None, 16, 3)
+    s.synchronize()
+    assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(tx.cpu().numpy(), pos, None, 16, 3)) < TOL
+
+
+def test_input_validation_raises():
+    pos = torch.rand(10, 2, device=DEV) - 0.5
+    x = torch.rand(10, device=DEV)
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(x, pos.double(), None, 16, 3)  # pos must be float32 (core_cuda.cu:49)
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(x, torch.rand(10, 4, device=DEV), None, 16, 3)  # d <= 3 (core_cuda.cu:53)
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(x[:5], pos, None, 16, 3)  # x.size(0) == n (core_cuda.cu:83)
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(x.double(), pos, None, 16, 3)  # float32 | complex64 (core_cuda.cu:77-79)
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(x, pos, torch.zeros(10, device=DEV, dtype=torch.int32), 16, 3)  # batch int64
+    with pytest.raises(RuntimeError):
+        T.nfft_forward(torch.rand(1, 16, 8, device=DEV), pos, None, 3)  # all frequency dims == N
+    with pytest.raises(RuntimeError):
+        T.nfft_forward(torch.rand(2, 16, 16, device=DEV), pos, None, 3)  # x.size(0) == batch size
+    with pytest.raises(RuntimeError):
+        T.nfft_fastsum(x, torch.rand(16, device=DEV), pos)  # coeffs must be d-dimensional
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(x, pos, None, 16, 9)  # cutoff range
+
+
+# ---------------------------------------------------------------------------------------------
+# approximation error against the exact NDFT: no worse than the reference's algorithm at each m
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,N", [(1, 64), (2, 32), (3, 16)])
+@pytest.mark.parametrize("m", [2, 3, 4, 6])
+def test_error_vs_ndft_not_worse_than_reference_algorithm(d, N, m):
+    if m >= N // 2:
+        pytest.skip("m < N/2")
+    rng = np.random.default_rng(d * 10 + m)
+    pos, batch = make_points(rng, d, 2, 300)
+    x = make_values(rng, (600, 2), False)
+    exact = O.ndft_adjoint(x, pos, batch, N)
+    ours = O.rel_l2(T.nfft_adjoint(cuda(x), cuda(pos), cuda(batch), N, m).cpu().numpy(), exact)
+    theirs = O.rel_l2(O.nfft_adjoint(x, pos, batch, N, m, prec="f64"), exact)
+    assert ours <= theirs * 1.05 + 2e-6
+    xh = make_values(rng, (2,) + (N,) * d + (2,), True)
+    exact = O.ndft_forward(xh, pos, batch)
+    ours = O.rel_l2(T.nfft_forward(cuda(xh), cuda(pos), cuda(batch), m).cpu().numpy(), exact)
+    theirs = O.rel_l2(O.nfft_forward(xh, pos, batch, m, prec="f64"), exact)
+    assert ours <= theirs * 1.05 + 2e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------
+FULL = {
+    "c2": (1, 1024, 8, 2 ** 20, 64, 1),
+    "c3": (2, 256, 4, 2 ** 23, 16, 8),
+    "c4": (3, 128, 4, 2 ** 24, 4, 1),
+}
+
+
+def _full_inputs(name, clustered=False):
+    d, N, m, n, B, C = FULL[name]
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0)
+    if clustered:
+        centers = torch.rand(64, d, device=DEV, generator=gen) * 0.8 - 0.4
+        ids = torch.randint(0, 64, (n,), device=DEV, generator=gen)
+        pos = centers[ids] + 0.02 * torch.randn(n, d, device=DEV, generator=gen)
+        pos = ((pos + 0.5) % 1.0) - 0.5
+    else:
+        pos = torch.rand(n, d, device=DEV, generator=gen) - 0.5
+    x = torch.randn(n, C, device=DEV, generator=gen)
+    batch = torch.arange(n, device=DEV) // (n // B)
+    return d, N, m, n, B, C, pos.contiguous(), x, batch
+
+
+@pytest.mark.parametrize("name,clustered", [("c2", False), ("c3", False), ("c4", False), ("c4", True)])
+def test_full_size_properties(name, clustered):
+    d, N, m, n, B, C, pos, x, batch = _full_inputs(name, clustered)
+    y = T.nfft_adjoint(x, pos, batch, N, m, batch_size=B)
+    assert y.shape == (B,) + (N,) * d + (C,)
+    # (1) zero frequency = plain sum of the values of each point set (exact for the NDFT)
+    zero = y[(slice(None),) + (N // 2,) * d]
+    sums = torch.zeros(B, C, device=DEV, dtype=torch.float64).index_add_(0, batch, x.double())
+    scale = x.double().pow(2).sum().sqrt()
+    assert float((zero.real.double() - sums).abs().max() / scale) < 1e-3
+    # (2) Hermitian symmetry of the spectrum of real data: y[-k] = conj(y[k]) for |k| < N/2
+    inner = (slice(None),) + (slice(1, None),) * d
+    flipped = torch.flip(y[inner], dims=list(range(1, d + 1))).conj()
+    assert float((y[inner] - flipped).abs().max() / y.abs().max()) < 1e-4
+    # (3) linearity in x
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(1)
+    x2 = torch.randn(n, C, device=DEV, generator=gen)
+    y2 = T.nfft_adjoint(x2, pos, batch, N, m, batch_size=B)
+    y12 = T.nfft_adjoint(2.5 * x - x2, pos, batch, N, m, batch_size=B)
+    assert float(torch.linalg.vector_norm(y12 - (2.5 * y - y2)) / torch.linalg.vector_norm(y12)) < TOL
+    del y12, y2
+    # (4) forward of a single frequency is a plane wave: exp(-2 pi i k . pos)
+    xh = torch.zeros_like(y)
+    k = (1, -2, 3)[:d]
+    xh[(slice(None),) + tuple(N // 2 + kk for kk in k)] = 1.0
+    f = T.nfft_forward(xh, pos, batch, m, batch_size=B)
+    phase = -2 * np.pi * sum(kk * pos[:, a].double() for a, kk in enumerate(k))
+    wave = torch.polar(torch.ones_like(phase), phase)
+    bound = 5e-4 if m <= 4 else 2e-5  # the NFFT's own error at this cutoff
+    assert float((f.reshape(n, C).to(torch.complex128) - wave[:, None]).abs().max()) < bound
+    del f, xh
+    # (5) adjointness: <adjoint(x), yh> = <x, forward(yh)>, and the C2R path equals Re of the C2C path
+    gen.manual_seed(2)
+    yh = torch.complex(torch.randn(y.shape, device=DEV, generator=gen), torch.randn(y.shape, device=DEV, generator=gen))
+    fy = T.nfft_forward(yh, pos, batch, m, batch_size=B)
+    lhs = torch.sum(yh.conj().to(torch.complex128) * y.to(torch.complex128))
+    rhs = torch.sum(fy.reshape(n, C).conj().to(torch.complex128) * x.to(torch.complex128))
+    assert float((lhs - rhs).abs() / lhs.abs()) < 1e-5
+    fr = T.nfft_forward(yh, pos, batch, m, real_output=True, batch_size=B)
+    assert float(torch.linalg.vector_norm(fr - fy.real) / torch.linalg.vector_norm(fr)) < TOL
