@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the NFFT hot path (BASELINE.json: NU points/sec, adjoint + forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c4|c4_clustered|c3|c2] [--ref-device cuda|cpu]
+
+One "step" = one adjoint NFFT (real x -> complex spectrum) followed by one forward NFFT
+(spectrum -> real values at the same points) of the workload, i.e. pts/s = n / (t_adj + t_fwd).
+Default workload (N = 1 and per GPU for N > 1): BASELINE configs[3] "c4": 3D, N=128, m=4,
+n=2^24 uniform points, batch_size=4, 1 channel -- the configuration the north-star target is
+quoted on.  For N > 1 every rank transforms its own 4 batch entries (batch sharding, no
+data-path collective): weak scaling.
+
+Printed JSON (rank 0, one line): see the keys below.  `value` has inputs resident in HBM;
+`e2e` goes through the public API with pinned HOST buffers (H2D of pos/x/batch and D2H of both
+results inside the timed region).  `roofline` is for the dominant kernel (spread), from CUDA
+events recorded inside the library around that stage during the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (d, N, m, n_total, B, C, distribution)
+    "c2": (1, 1024, 8, 2 ** 20, 64, 1, "uniform"),
+    "c3": (2, 256, 4, 2 ** 23, 16, 8, "uniform"),
+    "c4": (3, 128, 4, 2 ** 24, 4, 1, "uniform"),
+    "c4_clustered": (3, 128, 4, 2 ** 24, 4, 1, "clustered"),
+    "c4_small": (3, 128, 4, 2 ** 20, 4, 1, "uniform"),
+}
+
+
+def algorithmic_bytes(d, N, n, B, C):
+    """compulsory HBM traffic with real-data FFTs."""
+    M = 2 * N
+    G_r = B * C * M ** d * 4
+    G_h = B * C * M ** (d - 1) * (M // 2 + 1) * 8
+    Y_c = B * C * N ** d * 8
+    Y_h = B * C * N ** (d - 1) * (N // 2 + 1) * 8
+    adj = n * (4 * d + 4 * C + 8) + G_r + (G_r + G_h) + (Y_h + Y_c)
+    fwd = (Y_c + G_h) + (G_h + G_r) + G_r + n * (4 * d + 8) + 4 * n * C
+    spread = n * (4 * d + 4 * C + 8) + G_r       # pos + x + batch read, real grid written
+    gather = G_r + n * (4 * d + 8) + 4 * n * C   # grid read, pos + batch read, y written
+    return {"adjoint": adj, "forward": fwd, "spread": spread, "gather": gather}
+
+
+def make_inputs(torch, workload, device, seed):
+    d, N, m, n, B, C, distribution = WORKLOADS[workload]
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    if distribution == "uniform":
+        pos = torch.rand(n, d, device=device, generator=gen) - 0.5
+    else:  # 64 Gaussian clusters, sigma 0.02, wrapped into the torus
+        centers = torch.rand(64, d, device=device, generator=gen) * 0.8 - 0.4
+        ids = torch.randint(0, 64, (n,), device=device, generator=gen)
+        pos = centers[ids] + 0.02 * torch.randn(n, d, device=device, generator=gen)
+        pos = ((pos + 0.5) % 1.0) - 0.5
+    x = torch.randn(n, C, device=device, generator=gen)
+    batch = torch.arange(n, device=device) // (n // B)
+    return pos.contiguous(), x.contiguous(), batch.contiguous()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_ndft(workload, sample_points=192):
+    """The reference's only host path: exact NDFT direct sums (reference torch_nfft/ndft.py:5-44),
+    timed on this box's host cores on a bounded sample of the workload's point set."""
+    import torch
+    d, N, m, n, B, C, _ = WORKLOADS[workload]
+    kind = "reference"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref", "torch_nfft"))
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_ndft", os.path.join(ROOT, "baseline", "_ref", "torch_nfft", "ndft.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        adj, fwd = mod.ndft_adjoint, mod.ndft_forward
+    except Exception:
+        from oracle import nfft_oracle as O  # port of the same direct sums (numpy)
+        kind = "port"
+        adj = lambda x, pos, batch, N: torch.from_numpy(O.ndft_adjoint(x.numpy(), pos.numpy(), None, N))
+        fwd = lambda y, pos, batch: torch.from_numpy(O.ndft_forward(y.numpy(), pos.numpy(), None))
+    g = torch.Generator().manual_seed(0)
+    ns = sample_points
+    pos = torch.rand(ns, d, generator=g) - 0.5
+    x = torch.randn(ns, C, generator=g)
+    t0 = time.perf_counter()
+    y = adj(x, pos, None, N) if kind == "port" else adj(x, pos, None, N=N)
+    f = fwd(y, pos, None)
+    dt = time.perf_counter() - t0
+    return {"value": ns / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{ns} of the workload's points (one point set, {C} channel(s)), exact NDFT adjoint+forward "
+                      f"on the full {N}^{d} spectrum, {dt:.2f} s of CPU work"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torch_nfft_b200 as T
+    from torch_nfft_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    d, N, m, n, B, C, distribution = WORKLOADS[args.workload]
+
+    pos, x, batch = make_inputs(torch, args.workload, dev, seed=1234 + rank)
+    # pinned host copies for the end-to-end arm
+    h_pos, h_x, h_batch = (t.cpu().pin_memory() for t in (pos, x, batch))
+    h_spec = torch.empty((B,) + (N,) * d + (C,), dtype=torch.complex64).pin_memory()
+    h_y = torch.empty((n, C), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        y = T.nfft_adjoint(x, pos, batch, N, m, batch_size=B)
+        return T.nfft_forward(y, pos, batch, m, real_output=True, batch_size=B)
+
+    def step_e2e():
+        dpos = h_pos.to(dev, non_blocking=True)
+        dx = h_x.to(dev, non_blocking=True)
+        dbatch = h_batch.to(dev, non_blocking=True)
+        y = T.nfft_adjoint(dx, dpos, dbatch, N, m, batch_size=B)
+        f = T.nfft_forward(y, dpos, dbatch, m, real_output=True, batch_size=B)
+        h_spec.copy_(y, non_blocking=True)
+        h_y.copy_(f, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    launches0 = _lib.launch_count()
+    ms_total, t0, t1 = timed(step_device, args.steps)
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        alg = algorithmic_bytes(d, N, n, B, C)
+        peak, peak_src = measured_peak_gbs()
+        spread_ms = prof["spread"][0] / max(prof["spread"][1], 1)
+        gather_ms = prof["gather"][0] / max(prof["gather"][1], 1)
+        achieved = alg["spread"] / (spread_ms * 1e-3) / 1e9
+        stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
+        taps = n * C * (2 * m + 2) ** d
+        out = {
+            "metric": "NU points/sec (adjoint+forward)",
+            "value": n * world / (ms_step * 1e-3),
+            "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {d}D adjoint+forward NFFT, N={N}, m={m}, n={n} {distribution} "
+                                   f"points per GPU, batch_size={B}, {C} channel(s), real x -> complex spectrum -> real y",
+                       "sharding": "batch entries per GPU, no collective" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (pos+x+batch = %d MB per step, grid %d MB)" % (
+                           (n * (4 * d + 4 * C + 8)) >> 20, (B * C * (2 * N) ** d * 4) >> 20)},
+            "e2e": {"value": n * world / (ms_e2e / args.steps * 1e-3), "unit": "points/s",
+                    "h2d_bytes_per_step": n * (4 * d + 4 * C + 8),
+                    "d2h_bytes_per_step": B * C * N ** d * 8 + n * C * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "spread_kernel (adjoint window convolution)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg["spread"], "ms_per_launch": spread_ms,
+                         "whole_step": {"algorithmic_bytes": alg["adjoint"] + alg["forward"],
+                                        "achieved": (alg["adjoint"] + alg["forward"]) / (ms_step * 1e-3) / 1e9,
+                                        "frac": (alg["adjoint"] + alg["forward"]) / (ms_step * 1e-3) / 1e9 / peak},
+                         "gather": {"achieved": alg["gather"] / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
+                                    "ms_per_launch": gather_ms},
+                         "taps_per_s": {"spread": taps / (spread_ms * 1e-3), "gather": taps / (gather_ms * 1e-3) if gather_ms else None}},
+            "stage_ms_per_step": stage_ms,
+            "cpu_baseline": cpu_baseline_ndft(args.workload) if world == 1 else None,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The unmodified reference (baseline/_ref): its CUDA NFFT through its own public API on the
+    same config (north_star: "next to the reference's CUDA NFFT on the same B200"), together with
+    its only CPU path (ndft) as cpu_baseline.  Falls back to the CPU path alone without CUDA."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    d, N, m, n, B, C, distribution = WORKLOADS[args.workload]
+    cpu = cpu_baseline_ndft(args.workload)
+    base = {"impl": "reference", "metric": "NU points/sec (adjoint+forward)", "unit": "points/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {d}D adjoint+forward NFFT, N={N}, m={m}, n={n} {distribution} points, "
+                                   f"batch_size={B}, {C} channel(s)"},
+            "cpu_baseline": cpu}
+    ref = None
+    if args.ref_device == "cuda" and torch.cuda.is_available():
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+            import torch_nfft as ref  # noqa
+        except Exception as e:  # pragma: no cover
+            base["reference_cuda_unavailable"] = repr(e)[:200]
+            ref = None
+    if ref is None:
+        base.update({"value": cpu["value"], "ms_per_step": None, "gpu_launches": 0,
+                     "e2e": {"value": cpu["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "config": dict(base["config"], arm="reference CPU path (ndft direct sums), bounded sample")})
+        print(json.dumps(base))
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    pos, x, batch = make_inputs(torch, args.workload, dev, seed=1234)
+
+    def step():
+        y = ref.nfft_adjoint(x, pos, batch, N, m)
+        return ref.nfft_forward(y, pos, batch, m, True)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    v = n / (ms_step * 1e-3)
+    base.update({"value": v, "ms_per_step": ms_step, "gpu_launches": 0,
+                 "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "config": dict(base["config"], arm="reference CUDA NFFT (baseline/_ref, torch_nfft.nfft_adjoint + "
+                                                    "nfft_forward), inputs resident on the GPU")})
+    print(json.dumps(base))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

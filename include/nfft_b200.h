@@ -129,6 +129,12 @@ int nfftb200_sort_points(const float* pos, const int64_t* batch, uint32_t* keys_
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n,
                             int32_t* out);
 
+/* Optional per-stage timing with CUDA events recorded on the caller's stream around each stage.
+ * read: ms_out[8], count_out[8] in stage order sort, spread, fft, unpack, pack, gather, multiply,
+ * memset; call after synchronising the stream.  Used by bench.py for the roofline numbers. */
+void nfftb200_profile_enable(int on);
+int nfftb200_profile_read(double* ms_out, int64_t* count_out);
+
 /* Destroys cached cuFFT plans (all devices). */
 int nfftb200_plan_cache_clear(void);
 

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "nfftb200_last_error": (ctypes.c_char_p, []),
     "nfftb200_launch_count": (_i64, []),
     "nfftb200_plan_cache_clear": (ctypes.c_int, []),
+    "nfftb200_profile_enable": (None, [_i32]),
+    "nfftb200_profile_read": (_i32, [_vp, _vp]),
     "nfftb200_debug_geometry": (_i32, [_i32, _i64, _i32, _i64, _i64, _i32, _i64, _vp]),
     "nfftb200_workspace_bytes": (_sz, [_i32, _i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32]),
     # (pos, x, batch, y, n, d, N, m, B, C, flags, ws, ws_bytes, stream)
@@ -85,3 +87,18 @@ def geometry(d, N, m, B=1, C=1, flags=0, n=0):
     out = (ctypes.c_int32 * 20)()
     check(lib().nfftb200_debug_geometry(d, N, m, B, C, flags, n, ctypes.cast(out, ctypes.c_void_p)), "geometry")
     return dict(zip(GEOMETRY_FIELDS, list(out)))
+
+
+STAGES = ("sort", "spread", "fft", "unpack", "pack", "gather", "multiply", "memset")
+
+
+def profile_enable(on: bool):
+    lib().nfftb200_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{stage: (total_ms, calls)} since the last read; synchronise the stream first."""
+    ms = (ctypes.c_double * 8)()
+    cnt = (ctypes.c_int64 * 8)()
+    check(lib().nfftb200_profile_read(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(cnt, ctypes.c_void_p)), "profile_read")
+    return {s: (ms[i], int(cnt[i])) for i, s in enumerate(STAGES)}

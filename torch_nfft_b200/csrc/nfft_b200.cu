@@ -10,15 +10,49 @@
 #include "spectral.cuh"
 #include "window.cuh"
 
+#include <initializer_list>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <vector>
 
+
 namespace nfftb200 {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+// ----------------------------------------------------------------------------------------
+// optional per-stage timing with CUDA events on the caller's stream (bench.py roofline)
+// ----------------------------------------------------------------------------------------
+enum Stage { ST_SORT = 0, ST_SPREAD, ST_FFT, ST_UNPACK, ST_PACK, ST_GATHER, ST_MULTIPLY, ST_MEMSET, ST_COUNT };
+struct ProfSpan { int stage; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::mutex g_prof_mutex;
+static std::vector<ProfSpan> g_prof_spans;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+struct ProfScope {
+    ProfSpan span{};
+    cudaStream_t st;
+    bool on;
+    ProfScope(int stage, cudaStream_t s) : st(s), on(g_prof_on) {
+        if (!on) return;
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        for (cudaEvent_t* e : {&span.a, &span.b}) {
+            if (!g_prof_pool.empty()) { *e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+            else if (cudaEventCreate(e) != cudaSuccess) { on = false; return; }
+        }
+        span.stage = stage;
+        cudaEventRecord(span.a, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(span.b, st);
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        g_prof_spans.push_back(span);
+    }
+};
 
 // ----------------------------------------------------------------------------------------
 // geometry
@@ -258,15 +292,22 @@ static unsigned blocks_for(long long total, int threads = 256) { return (unsigne
 // ----------------------------------------------------------------------------------------
 static int do_spread(const Geom& g, const float* pos, const float* x, const int64_t* batch, float* grid, long long n,
                      char* sort_ws, SortPlan* sp_out, cudaStream_t st) {
-    NF_CUDA(cudaMemsetAsync(grid, 0, (size_t)g.B * g.C * g.Md * (g.cplx ? 8 : 4), st));
+    {
+        ProfScope ps(ST_MEMSET, st);
+        NF_CUDA(cudaMemsetAsync(grid, 0, (size_t)g.B * g.C * g.Md * (g.cplx ? 8 : 4), st));
+    }
     SortPlan sp{};
-    NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
+    {
+        ProfScope ps(ST_SORT, st);
+        NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
+    }
     if (sp_out) *sp_out = sp;
     if (n == 0) return NFFTB200_OK;
     WindowArgs a{};
     a.pos = pos;
     a.xin = x;
     a.grid = grid;
+    ProfScope ps(ST_SPREAD, st);
     return launch_window(true, g, a, sp, st);
 }
 
@@ -277,12 +318,14 @@ static int do_gather(const Geom& g, const float* pos, const int64_t* batch, cons
     if (presorted) {
         sp = *presorted;
     } else {
+        ProfScope ps(ST_SORT, st);
         NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
     }
     WindowArgs a{};
     a.pos = pos;
     a.yout = y;
     a.grid = const_cast<float*>(grid);
+    ProfScope ps(ST_GATHER, st);
     return launch_window(false, g, a, sp, st);
 }
 
@@ -338,13 +381,21 @@ static int do_adjoint_finish(const Geom& g, float* grid, float* y, bool real_out
     if (!g.cplx) {
         NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_R2C, &plan));
         NF_CUFFT(cufftSetStream(plan, st));
-        NF_CUFFT(cufftExecR2C(plan, grid, reinterpret_cast<cufftComplex*>(spec)));
+        {
+            ProfScope ps(ST_FFT, st);
+            NF_CUFFT(cufftExecR2C(plan, grid, reinterpret_cast<cufftComplex*>(spec)));
+        }
+        ProfScope ps(ST_UNPACK, st);
         return NF_DIM_DISPATCH(launch_unpack, g, true, real_out, spec, y, st);
     }
     NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2C, &plan));
     NF_CUFFT(cufftSetStream(plan, st));
-    NF_CUFFT(cufftExecC2C(plan, reinterpret_cast<cufftComplex*>(grid), reinterpret_cast<cufftComplex*>(grid),
-                          CUFFT_INVERSE));  // sign +, core_cuda.cu:267
+    {
+        ProfScope ps(ST_FFT, st);
+        NF_CUFFT(cufftExecC2C(plan, reinterpret_cast<cufftComplex*>(grid), reinterpret_cast<cufftComplex*>(grid),
+                              CUFFT_INVERSE));  // sign +, core_cuda.cu:267
+    }
+    ProfScope ps(ST_UNPACK, st);
     return NF_DIM_DISPATCH(launch_unpack, g, false, real_out, reinterpret_cast<const float2*>(grid), y, st);
 }
 
@@ -353,15 +404,23 @@ static int do_forward_begin(const Geom& g, const float* xhat, bool xreal, bool r
                             cudaStream_t st) {
     cufftHandle plan;
     if (real_out) {
-        NF_TRY(NF_DIM_DISPATCH(launch_pack, g, true, xreal, xhat, spec, st));
+        {
+            ProfScope ps(ST_PACK, st);
+            NF_TRY(NF_DIM_DISPATCH(launch_pack, g, true, xreal, xhat, spec, st));
+        }
         NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2R, &plan));
         NF_CUFFT(cufftSetStream(plan, st));
+        ProfScope ps(ST_FFT, st);
         NF_CUFFT(cufftExecC2R(plan, reinterpret_cast<cufftComplex*>(spec), grid));
         return NFFTB200_OK;
     }
-    NF_TRY(NF_DIM_DISPATCH(launch_pack, g, false, xreal, xhat, reinterpret_cast<float2*>(grid), st));
+    {
+        ProfScope ps(ST_PACK, st);
+        NF_TRY(NF_DIM_DISPATCH(launch_pack, g, false, xreal, xhat, reinterpret_cast<float2*>(grid), st));
+    }
     NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2C, &plan));
     NF_CUFFT(cufftSetStream(plan, st));
+    ProfScope ps(ST_FFT, st);
     NF_CUFFT(cufftExecC2C(plan, reinterpret_cast<cufftComplex*>(grid), reinterpret_cast<cufftComplex*>(grid),
                           CUFFT_FORWARD));  // sign -, core_cuda.cu:445
     return NFFTB200_OK;
@@ -373,18 +432,32 @@ static int do_fastsum_middle(const Geom& g, float* grid, const float* coeffs, bo
     if (!g.cplx) {
         NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_R2C, &plan));
         NF_CUFFT(cufftSetStream(plan, st));
-        NF_CUFFT(cufftExecR2C(plan, grid, reinterpret_cast<cufftComplex*>(spec)));
-        NF_TRY(NF_DIM_DISPATCH(launch_multiply, g, true, creal, spec, coeffs, st));
+        {
+            ProfScope ps(ST_FFT, st);
+            NF_CUFFT(cufftExecR2C(plan, grid, reinterpret_cast<cufftComplex*>(spec)));
+        }
+        {
+            ProfScope ps(ST_MULTIPLY, st);
+            NF_TRY(NF_DIM_DISPATCH(launch_multiply, g, true, creal, spec, coeffs, st));
+        }
         NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2R, &plan));
         NF_CUFFT(cufftSetStream(plan, st));
+        ProfScope ps(ST_FFT, st);
         NF_CUFFT(cufftExecC2R(plan, reinterpret_cast<cufftComplex*>(spec), grid));
         return NFFTB200_OK;
     }
     NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2C, &plan));
     NF_CUFFT(cufftSetStream(plan, st));
     cufftComplex* gc = reinterpret_cast<cufftComplex*>(grid);
-    NF_CUFFT(cufftExecC2C(plan, gc, gc, CUFFT_INVERSE));
-    NF_TRY(NF_DIM_DISPATCH(launch_multiply, g, false, creal, reinterpret_cast<float2*>(grid), coeffs, st));
+    {
+        ProfScope ps(ST_FFT, st);
+        NF_CUFFT(cufftExecC2C(plan, gc, gc, CUFFT_INVERSE));
+    }
+    {
+        ProfScope ps(ST_MULTIPLY, st);
+        NF_TRY(NF_DIM_DISPATCH(launch_multiply, g, false, creal, reinterpret_cast<float2*>(grid), coeffs, st));
+    }
+    ProfScope ps(ST_FFT, st);
     NF_CUFFT(cufftExecC2C(plan, gc, gc, CUFFT_FORWARD));
     return NFFTB200_OK;
 }
@@ -433,6 +506,31 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
     int v[20] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
                  g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads};
     for (int i = 0; i < 20; ++i) out[i] = v[i];
+    return NFFTB200_OK;
+}
+
+void nfftb200_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_on = on != 0;
+}
+
+// Accumulates the elapsed milliseconds and call counts of all recorded stage spans into
+// ms_out[8] / count_out[8] (stage order: sort, spread, fft, unpack, pack, gather, multiply, memset)
+// and clears the record.  The caller must have synchronised the stream(s).
+int nfftb200_profile_read(double* ms_out, int64_t* count_out) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (int i = 0; i < ST_COUNT; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+    for (const ProfSpan& sp : g_prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            ms_out[sp.stage] += ms;
+            count_out[sp.stage] += 1;
+        }
+        g_prof_pool.push_back(sp.a);
+        g_prof_pool.push_back(sp.b);
+    }
+    g_prof_spans.clear();
+    (void)cudaGetLastError();
     return NFFTB200_OK;
 }
 
