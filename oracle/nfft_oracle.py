@@ -185,15 +185,11 @@ def _band_index(N, M):
 # --------------------------------------------------------------------------------------
 # the three transforms
 # --------------------------------------------------------------------------------------
-def nfft_adjoint(x, pos, batch=None, N=16, m=3, real_output=False, prec="f32"):
-    """Restates nfft_adjoint_cuda (csrc/cuda/core_cuda.cu:144-336):
-    spread -> unnormalised FFT with sign + (CUFFT_INVERSE, :267) -> crop/fftshift/deconvolve
-    into y[B, N..N, *cols] (:298-326)."""
-    pos, batch, B = _as_points(pos, batch)
-    n, d = pos.shape
-    x2, cols, C = _columns(x, n)
+def adjoint_finish(g, N, m, cols, real_output=False, prec="f32"):
+    """grid [B, C, M..M] -> y [B, N..N, *cols]: FFT(+) (core_cuda.cu:267) and roll-off/crop (:298-326)."""
+    B, C = g.shape[:2]
+    d = g.ndim - 2
     M = 2 * N
-    g = spread(pos, x2, batch, B, N, m, prec)
     axes = tuple(range(2, 2 + d))
     ghat = np.fft.ifftn(g, axes=axes) * float(M ** d)  # sum_j g_j e^{+2 pi i jk/M}
     if prec == "f32":
@@ -209,6 +205,37 @@ def nfft_adjoint(x, pos, batch=None, N=16, m=3, real_output=False, prec="f32"):
     return y.astype(np.complex64 if prec == "f32" else np.complex128)
 
 
+def nfft_adjoint(x, pos, batch=None, N=16, m=3, real_output=False, prec="f32"):
+    """Restates nfft_adjoint_cuda (csrc/cuda/core_cuda.cu:144-336):
+    spread -> unnormalised FFT with sign + (CUFFT_INVERSE, :267) -> crop/fftshift/deconvolve
+    into y[B, N..N, *cols] (:298-326)."""
+    pos, batch, B = _as_points(pos, batch)
+    n, d = pos.shape
+    x2, cols, C = _columns(x, n)
+    g = spread(pos, x2, batch, B, N, m, prec)
+    return adjoint_finish(g, N, m, cols, real_output, prec)
+
+
+def forward_begin(xhat, d, m, prec="f32"):
+    """xhat [B, N..N, *cols] -> complex grid [B, C, M..M]: roll-off + zero-pad (core_cuda.cu:403-420)
+    and FFT(-) (:445)."""
+    xhat = np.asarray(xhat)
+    B, N = xhat.shape[0], xhat.shape[1]
+    assert xhat.ndim >= d + 1 and all(s == N for s in xhat.shape[1:1 + d])  # core_cuda.cu:104-114
+    cols = xhat.shape[1 + d:]
+    C = int(np.prod(cols)) if len(cols) else 1
+    M = 2 * N
+    xh = np.moveaxis(xhat.reshape((B,) + (N,) * d + (C,)), -1, 1)  # [B, C, N..N]
+    f = rolloff_factors(N, m, d, prec)
+    cdt = np.complex64 if prec == "f32" else np.complex128
+    vals = (xh.astype(cdt) * f[None, None]).astype(cdt)
+    ghat = np.zeros((B, C) + (M,) * d, dtype=np.complex128)
+    bi = _band_index(N, M)
+    ghat[(slice(None), slice(None)) + np.ix_(*([bi] * d))] = vals
+    g = np.fft.fftn(ghat, axes=tuple(range(2, 2 + d)))
+    return g.astype(np.complex64) if prec == "f32" else g
+
+
 def nfft_forward(xhat, pos, batch=None, m=3, real_output=False, prec="f32"):
     """Restates nfft_forward_cuda (core_cuda.cu:340-531): deconvolve + zero-pad into the
     oversampled grid (:403-420), unnormalised FFT with sign - (CUFFT_FORWARD, :445), gather."""
@@ -217,21 +244,9 @@ def nfft_forward(xhat, pos, batch=None, m=3, real_output=False, prec="f32"):
     xhat = np.asarray(xhat)
     assert xhat.ndim >= d + 1 and xhat.shape[0] == B  # core_cuda.cu:104-106
     N = xhat.shape[1]
-    assert all(s == N for s in xhat.shape[1:1 + d])
     cols = xhat.shape[1 + d:]
-    C = int(np.prod(cols)) if len(cols) else 1
-    M = 2 * N
-    xh = xhat.reshape((B,) + (N,) * d + (C,))
-    xh = np.moveaxis(xh, -1, 1)  # [B, C, N..N]
-    f = rolloff_factors(N, m, d, prec)
     cdt = np.complex64 if prec == "f32" else np.complex128
-    vals = (xh.astype(cdt) * f[None, None]).astype(cdt)
-    ghat = np.zeros((B, C) + (M,) * d, dtype=np.complex128)
-    bi = _band_index(N, M)
-    ghat[(slice(None), slice(None)) + np.ix_(*([bi] * d))] = vals
-    g = np.fft.fftn(ghat, axes=tuple(range(2, 2 + d)))
-    if prec == "f32":
-        g = g.astype(np.complex64)
+    g = forward_begin(xhat, d, m, prec)
     y = gather(g, pos, batch, N, m, prec)
     y = y.reshape((n,) + tuple(cols))
     if real_output:
@@ -239,24 +254,13 @@ def nfft_forward(xhat, pos, batch=None, m=3, real_output=False, prec="f32"):
     return y.astype(cdt)
 
 
-def nfft_fastsum(x, coeffs, sources, targets=None, source_batch=None, target_batch=None,
-                 m=3, prec="f32"):
-    """Restates nfft_fastsum_cuda (core_cuda.cu:535-852): spread sources, FFT(+), multiply
-    in-band entries by (prod phi_hat_inv)^2 * coeffs[k+N/2] and zero the rest
-    (spectral_window_operations.cu:292-331), FFT(-), gather at targets.  Output dtype follows
-    x (real x -> real part, core_cuda.cu:814-818)."""
-    if targets is None:
-        targets, target_batch = sources, source_batch
-    sources, source_batch, B = _as_points(sources, source_batch)
-    targets, target_batch, Bt = _as_points(targets, target_batch)
-    assert B == Bt and sources.shape[1] == targets.shape[1]
-    n, d = sources.shape
-    x2, cols, C = _columns(x, n)
+def fastsum_middle(g, coeffs, m, prec="f32"):
+    """grid -> grid: FFT(+), multiply in-band entries by (prod phi_hat_inv)^2 * coeffs[k+N/2] and zero
+    the rest (spectral_window_operations.cu:292-331), FFT(-)  (core_cuda.cu:683-765)."""
     coeffs = np.asarray(coeffs)
-    assert coeffs.ndim == d
+    d = coeffs.ndim
     N = coeffs.shape[0]
     M = 2 * N
-    g = spread(sources, x2, source_batch, B, N, m, prec)
     axes = tuple(range(2, 2 + d))
     ghat = np.fft.ifftn(g, axes=axes) * float(M ** d)
     cdt = np.complex64 if prec == "f32" else np.complex128
@@ -269,8 +273,26 @@ def nfft_fastsum(x, coeffs, sources, targets=None, source_batch=None, target_bat
     out = np.zeros_like(ghat, dtype=np.complex128)
     out[sel] = (ghat[sel] * coeffs.astype(cdt)[None, None]).astype(cdt) * f2[None, None]
     g2 = np.fft.fftn(out, axes=axes)
-    if prec == "f32":
-        g2 = g2.astype(cdt)
+    return g2.astype(cdt) if prec == "f32" else g2
+
+
+def nfft_fastsum(x, coeffs, sources, targets=None, source_batch=None, target_batch=None,
+                 m=3, prec="f32"):
+    """Restates nfft_fastsum_cuda (core_cuda.cu:535-852): spread sources, fastsum_middle, gather at
+    targets.  Output dtype follows x (real x -> real part, core_cuda.cu:814-818)."""
+    if targets is None:
+        targets, target_batch = sources, source_batch
+    sources, source_batch, B = _as_points(sources, source_batch)
+    targets, target_batch, Bt = _as_points(targets, target_batch)
+    assert B == Bt and sources.shape[1] == targets.shape[1]
+    n, d = sources.shape
+    x2, cols, C = _columns(x, n)
+    coeffs = np.asarray(coeffs)
+    assert coeffs.ndim == d
+    N = coeffs.shape[0]
+    cdt = np.complex64 if prec == "f32" else np.complex128
+    g = spread(sources, x2, source_batch, B, N, m, prec)
+    g2 = fastsum_middle(g, coeffs, m, prec)
     y = gather(g2, targets, target_batch, N, m, prec).reshape((targets.shape[0],) + tuple(cols))
     if np.iscomplexobj(x):
         return y.astype(cdt)

@@ -57,19 +57,76 @@ struct ProfScope {
 // ----------------------------------------------------------------------------------------
 // geometry
 // ----------------------------------------------------------------------------------------
-static int conflict_score(int dim, int L, int sY, int sZ, int nthreads) {
-    // number of extra wavefronts (bank conflicts) over all warps for the access pattern
-    // lane t -> offset (t % L) * s0 + (t / L) * s1 used by the spread team and the gather lanes
-    int score = 0;
+// Extra shared-memory wavefronts (bank conflicts) per warp-wide tile access, averaged over the
+// access patterns of the two kernels:
+//   gather: lane t reads offset (t % L) * s0 + (t / L) * s1                      (stencil rows)
+//   spread: lane t owns class (t % L, t / L) and touches offset
+//           ((t % L - u) mod L) * s0 + ((t / L - v) mod L) * s1 for a point with first-tap
+//           residues (u, v) -- all L^2 residues are equally likely.
+// (3D: s0 = sY, s1 = sZ over (y, z); 2D: s0 = 1, s1 = sY over (x, y).)
+static double conflict_score(int dim, int L, int sY, int sZ) {
     const int s0 = dim == 3 ? sY : 1, s1 = dim == 3 ? sZ : sY;
-    for (int w0 = 0; w0 < nthreads; w0 += 32) {
-        int cnt[32] = {0};
-        for (int t = w0; t < w0 + 32 && t < L * L; ++t) cnt[((t % L) * s0 + (t / L) * s1) & 31]++;
-        int mx = 0;
-        for (int b = 0; b < 32; ++b) mx = cnt[b] > mx ? cnt[b] : mx;
-        score += mx > 0 ? mx - 1 : 0;
+    const int team = L * L;
+    auto warp_extra = [&](int u, int v) {
+        int extra = 0;
+        for (int w0 = 0; w0 < team; w0 += 32) {
+            int cnt[32] = {0};
+            for (int t = w0; t < w0 + 32 && t < team; ++t) {
+                const int a0 = ((t % L) - u + L) % L, a1 = ((t / L) - v + L) % L;
+                cnt[(a0 * s0 + a1 * s1) & 31]++;
+            }
+            int mx = 0;
+            for (int b = 0; b < 32; ++b) mx = cnt[b] > mx ? cnt[b] : mx;
+            extra += mx - 1;
+        }
+        return extra;
+    };
+    double spread = 0.0;
+    for (int u = 0; u < L; ++u)
+        for (int v = 0; v < L; ++v) spread += warp_extra(u, v);
+    spread /= (double)(L * L);
+    const double gather = warp_extra(0, 0);
+    const int nwarps = (team + 31) / 32;
+    return (spread + gather) / (2.0 * nwarps);
+}
+
+struct StrideKey {
+    int dim, L, P0, P1, P2;
+    bool operator<(const StrideKey& o) const {
+        return std::tie(dim, L, P0, P1, P2) < std::tie(o.dim, o.L, o.P0, o.P1, o.P2);
     }
-    return score;
+};
+static std::mutex g_stride_mutex;
+static std::map<StrideKey, std::pair<int, int>> g_strides;
+
+// shared-memory strides: trade padding against bank conflicts; cost = tile floats * (1 + extra
+// wavefronts per access).  Cached: the search is a few million integer ops.
+static void choose_strides(Geom& g) {
+    g.sY = g.P[0];
+    g.sZ = g.P[0] * g.P[1];
+    if (g.dim == 1) return;
+    std::lock_guard<std::mutex> lock(g_stride_mutex);
+    const StrideKey key{g.dim, g.L, g.P[0], g.P[1], g.P[2]};
+    auto it = g_strides.find(key);
+    if (it == g_strides.end()) {
+        double best = 1e300;
+        int bY = g.sY, bZ = g.sZ;
+        for (int sy = g.P[0]; sy < g.P[0] + 32; ++sy) {
+            if (g.dim == 2) {
+                const double cost = (double)sy * g.P[1] * (1.0 + conflict_score(2, g.L, sy, 0));
+                if (cost < best) { best = cost; bY = sy; bZ = sy * g.P[1]; }
+            } else {
+                for (int pad = 0; pad < 32; ++pad) {
+                    const int sz = sy * g.P[1] + pad;
+                    const double cost = (double)sz * g.P[2] * (1.0 + conflict_score(3, g.L, sy, sz));
+                    if (cost < best) { best = cost; bY = sy; bZ = sz; }
+                }
+            }
+        }
+        it = g_strides.emplace(key, std::make_pair(bY, bZ)).first;
+    }
+    g.sY = it->second.first;
+    g.sZ = it->second.second;
 }
 
 static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, bool cplx, int64_t n_points) {
@@ -129,28 +186,8 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     g.tiles_per_batch = g.nt[0] * g.nt[1] * g.nt[2];
     if ((long long)g.tiles_per_batch * B >= (1ll << 31)) NF_FAIL(NFFTB200_ERR_INVALID, "too many tiles");
 
-    // shared-memory strides: trade padding against bank conflicts of the team / lane pattern
-    // cost = tile floats * (1 + extra wavefronts per warp)
     const int team = d == 1 ? g.L : g.L * g.L;
-    const int nwarps = (team + 31) / 32;
-    g.sY = g.P[0];
-    g.sZ = g.P[0] * g.P[1];
-    if (d == 2) {
-        double best = 1e30;
-        for (int sy = g.P[0]; sy < g.P[0] + 32; ++sy) {
-            const double cost = (double)sy * g.P[1] * (nwarps + conflict_score(2, g.L, sy, 0, team)) / nwarps;
-            if (cost < best) { best = cost; g.sY = sy; }
-        }
-        g.sZ = g.sY * g.P[1];
-    } else if (d == 3) {
-        double best = 1e30;
-        for (int sy = g.P[0]; sy < g.P[0] + 32; ++sy)
-            for (int pad = 0; pad < 32; ++pad) {
-                const int sz = sy * g.P[1] + pad;
-                const double cost = (double)sz * g.P[2] * (nwarps + conflict_score(3, g.L, sy, sz, team)) / nwarps;
-                if (cost < best) { best = cost; g.sY = sy; g.sZ = sz; }
-            }
-    }
+    choose_strides(g);
     long long te = d == 1 ? g.P[0] : (d == 2 ? (long long)g.sY * g.P[1] : (long long)g.sZ * g.P[2]);
     g.tile_elems = (int)((te + 3) / 4 * 4);
 

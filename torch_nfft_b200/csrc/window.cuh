@@ -44,36 +44,71 @@ __device__ __forceinline__ int fast_div(int x, int d, float inv) {
     return q;
 }
 
-// Stage `cnt` points (sorted positions p0..p0+cnt) into shared memory:
-//   s_psi[(q*DIM + slot)*LP + l], s_rec[q*8 + {0,1,2}] = first-tap coordinate in the padded tile,
-//   s_rec[q*8 + 3] = original point index, s_rec[q*8 + 4 + slot] = first-tap coordinate mod L.
+// ------------------------------------------------------------------------------------------
+// Point staging.  Every round the CTA stages kSubBatch sorted points into shared memory:
+//   s_psi[(q*DIM + slot)*LP + l]   window taps of point q along slot (X, Y, Z), zero padded to LP
+//   s_rec[q] = { sx | sxmod << 16, sy | symod << 16, sz | szmod << 16, w }
+//     s*  = coordinate of the first tap inside the padded tile, s*mod = s* mod L
+//     w   = original point index (gather) or the bits of x[i, k0] (spread)
+// Global loads (perm -> pos / x, two dependent HBM accesses) are issued one round ahead into
+// registers (prefetch) so that their latency overlaps the previous round's tap loop.
+// ------------------------------------------------------------------------------------------
+constexpr int kMinThreads = 64;
 template <int DIM>
-__device__ __forceinline__ void stage_points(const Geom& g, const WindowArgs& a, long long p0, int cnt,
-                                             const int* tile_org, float* s_psi, int* s_rec) {
-    const int L = g.L, LP = g.LP;
-    for (int w = threadIdx.x; w < cnt * DIM; w += blockDim.x) {
-        const int q = w / DIM, slot = w - q * DIM;
-        const int api = DIM - 1 - slot;
-        const uint32_t i = a.perm[p0 + q];
-        const float p = a.pos[(size_t)i * DIM + api];
-        const int c = (int)floorf(p * (float)g.M);  // reference cell (spatial_window_operations.cu:50)
-        const int sh = c - g.m;                      // reference shift
-        const double base = (double)p * (double)g.M - (double)sh;
-        float* ps = s_psi + (q * DIM + slot) * LP;
-        for (int l = 0; l < L; ++l) {
-            const float t = (float)(base - (double)l);
-            ps[l] = expf(-(t * t) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+struct StageRegs {
+    static constexpr int kItems = (kSubBatch * DIM + kMinThreads - 1) / kMinThreads;
+    float p[kItems];
+    uint32_t idx[kItems];
+};
+
+template <int DIM>
+__device__ __forceinline__ void stage_prefetch(StageRegs<DIM>& r, const WindowArgs& a, long long p0, int cnt) {
+#pragma unroll
+    for (int k = 0; k < StageRegs<DIM>::kItems; ++k) {
+        const int w = threadIdx.x + k * blockDim.x;
+        if (w < cnt * DIM) {
+            const int q = w / DIM, slot = w - q * DIM;
+            const uint32_t i = a.perm[p0 + q];
+            r.idx[k] = i;
+            r.p[k] = a.pos[(size_t)i * DIM + (DIM - 1 - slot)];
         }
-        for (int l = L; l < LP; ++l) ps[l] = 0.f;
-        // first tap in padded-tile coordinates: wrapped cell - m - (tile origin)
-        int s0 = wrap_mod(c, g.M) - g.m - tile_org[slot];
-        s_rec[q * 8 + slot] = s0;
-        s_rec[q * 8 + 4 + slot] = s0 % L;
-        if (slot == 0) {
-            s_rec[q * 8 + 3] = (int)i;
-            if (DIM < 3) { s_rec[q * 8 + 2] = 0; s_rec[q * 8 + 6] = 0; }
-            if (DIM < 2) { s_rec[q * 8 + 1] = 0; s_rec[q * 8 + 5] = 0; }
-            s_rec[q * 8 + 7] = 0;
+    }
+}
+
+template <int DIM, int LC>
+__device__ __forceinline__ void stage_store(const StageRegs<DIM>& r, const Geom& g, int cnt, const int* tile_org,
+                                            float* s_psi, int* s_rec, bool store_index) {
+    const int L = LC ? LC : g.L, LP = g.LP;
+#pragma unroll
+    for (int k = 0; k < StageRegs<DIM>::kItems; ++k) {
+        const int w = threadIdx.x + k * blockDim.x;
+        if (w < cnt * DIM) {
+            const int q = w / DIM, slot = w - q * DIM;
+            const float p = r.p[k];
+            const int c = (int)floorf(p * (float)g.M);  // reference cell (spatial_window_operations.cu:50)
+            const int sh = c - g.m;                      // reference shift
+            const double base = (double)p * (double)g.M - (double)sh;
+            float* ps = s_psi + (q * DIM + slot) * LP;
+            if (LC) {
+#pragma unroll
+                for (int l = 0; l < (LC + 3) / 4 * 4; ++l) {
+                    const float t = (float)(base - (double)l);
+                    ps[l] = l < LC ? expf(-(t * t) * g.inv_b) * g.inv_sqrt_b_pi : 0.f;  // eval_phi, :24-28
+                }
+            } else {
+                for (int l = 0; l < LP; ++l) {
+                    const float t = (float)(base - (double)l);
+                    ps[l] = l < L ? expf(-(t * t) * g.inv_b) * g.inv_sqrt_b_pi : 0.f;
+                }
+            }
+            // first tap in padded-tile coordinates: wrapped cell - m - (tile origin)
+            const int s0 = wrap_mod(c, g.M) - g.m - tile_org[slot];
+            s_rec[q * 4 + slot] = s0 | ((s0 % L) << 16);
+            if (slot == 0) {
+                if (DIM < 3) s_rec[q * 4 + 2] = 0;
+                if (DIM < 2) s_rec[q * 4 + 1] = 0;
+                if (store_index) s_rec[q * 4 + 3] = (int)r.idx[k];
+            }
         }
     }
 }
@@ -174,37 +209,72 @@ spread_kernel(const Geom g, const WindowArgs a) {
     } else {
         c1 = tid / L; c0 = tid - c1 * L; active = tid < L * L;
     }
+
+    // values of the staged points: x[i, k0 .. k0+NCOMP) prefetched with the positions
+    constexpr int kXItems = (kSubBatch * NCOMP + kMinThreads - 1) / kMinThreads;
+    StageRegs<DIM> regs;
+    float xreg[kXItems];
+    auto prefetch = [&](long long p0, int cnt) {
+        stage_prefetch<DIM>(regs, a, p0, cnt);
+#pragma unroll
+        for (int k = 0; k < kXItems; ++k) {
+            const int w = tid + k * blockDim.x;
+            if (w < cnt * NCOMP) {
+                const int q = w / NCOMP, kk = w - q * NCOMP;
+                const uint32_t i = a.perm[p0 + q];
+                xreg[k] = (a.k0 + kk < g.K) ? a.xin[(size_t)i * g.K + a.k0 + kk] : 0.f;
+            }
+        }
+    };
+    {
+        const long long left = t.p_hi - t.p_lo;
+        prefetch(t.p_lo, (int)(left < kSubBatch ? left : kSubBatch));
+    }
     __syncthreads();
 
     for (long long p0 = t.p_lo; p0 < t.p_hi; p0 += kSubBatch) {
         const int cnt = (int)((t.p_hi - p0) < kSubBatch ? (t.p_hi - p0) : kSubBatch);
-        stage_points<DIM>(g, a, p0, cnt, s_org, s_psi, s_rec);
-        for (int w = tid; w < cnt * NCOMP; w += blockDim.x) {
-            const int q = w / NCOMP, k = w - q * NCOMP;
-            const uint32_t i = a.perm[p0 + q];
-            s_xv[w] = (a.k0 + k < g.K) ? a.xin[(size_t)i * g.K + a.k0 + k] : 0.f;
+        stage_store<DIM, LC>(regs, g, cnt, s_org, s_psi, s_rec, false);
+#pragma unroll
+        for (int k = 0; k < kXItems; ++k) {
+            const int w = tid + k * blockDim.x;
+            if (w < cnt * NCOMP) {
+                if (NCOMP == 1) s_rec[w * 4 + 3] = __float_as_int(xreg[k]);
+                else s_xv[w] = xreg[k];
+            }
         }
         __syncthreads();
+        {
+            const long long left = t.p_hi - (p0 + kSubBatch);
+            if (left > 0) prefetch(p0 + kSubBatch, (int)(left < kSubBatch ? left : kSubBatch));
+        }
         if (active) {
             for (int q = 0; q < cnt; ++q) {
-                const int4 st = *reinterpret_cast<const int4*>(s_rec + q * 8);
-                const int4 md = *reinterpret_cast<const int4*>(s_rec + q * 8 + 4);
+                const int4 rec = *reinterpret_cast<const int4*>(s_rec + q * 4);
                 const float* ps = s_psi + q * DIM * LP;
                 float v[NCOMP];
+                if (NCOMP == 1) {
+                    v[0] = __int_as_float(rec.w);
+                } else {
 #pragma unroll
-                for (int k = 0; k < NCOMP; ++k) v[k] = s_xv[q * NCOMP + k];
+                    for (int k = 0; k < NCOMP; ++k) v[k] = s_xv[q * NCOMP + k];
+                }
                 if (DIM == 3) {
-                    int ay = c0 - md.y; ay += ay < 0 ? L : 0;
-                    int az = c1 - md.z; az += az < 0 ? L : 0;
+                    int ay = c0 - (rec.y >> 16); ay += ay < 0 ? L : 0;
+                    int az = c1 - (rec.z >> 16); az += az < 0 ? L : 0;
                     const float wz = ps[2 * LP + az], wy = ps[LP + ay];
                     // reference product order: x * psi(dim 0 = Z) * psi(dim 1 = Y) * psi(dim 2 = X)
 #pragma unroll
                     for (int k = 0; k < NCOMP; ++k) v[k] = (v[k] * wz) * wy;
-                    float* row = tile + (st.z + az) * g.sZ + (st.y + ay) * g.sY + st.x;
+                    float* row = tile + ((rec.z & 0xffff) + az) * g.sZ + ((rec.y & 0xffff) + ay) * g.sY + (rec.x & 0xffff);
                     if (LC) {
-                        float wx[LC ? LC : 1];
+                        constexpr int LQ = LC ? (LC + 3) / 4 : 1;
+                        float wx[LQ * 4];
 #pragma unroll
-                        for (int l = 0; l < LC; ++l) wx[l] = ps[l];
+                        for (int l4 = 0; l4 < LQ; ++l4) {
+                            const float4 w4 = reinterpret_cast<const float4*>(ps)[l4];
+                            wx[4 * l4] = w4.x; wx[4 * l4 + 1] = w4.y; wx[4 * l4 + 2] = w4.z; wx[4 * l4 + 3] = w4.w;
+                        }
 #pragma unroll
                         for (int k = 0; k < NCOMP; ++k) {
                             float* r = row + (size_t)k * g.tile_elems;
@@ -227,19 +297,19 @@ spread_kernel(const Geom g, const WindowArgs a) {
                         }
                     }
                 } else if (DIM == 2) {
-                    int ax = c0 - md.x; ax += ax < 0 ? L : 0;
-                    int ay = c1 - md.y; ay += ay < 0 ? L : 0;
+                    int ax = c0 - (rec.x >> 16); ax += ax < 0 ? L : 0;
+                    int ay = c1 - (rec.y >> 16); ay += ay < 0 ? L : 0;
                     const float wy = ps[LP + ay], wx = ps[ax];
-                    float* cellp = tile + (st.y + ay) * g.sY + st.x + ax;
+                    float* cellp = tile + ((rec.y & 0xffff) + ay) * g.sY + (rec.x & 0xffff) + ax;
 #pragma unroll
                     for (int k = 0; k < NCOMP; ++k) {
                         float* r = cellp + (size_t)k * g.tile_elems;
                         *r = fmaf(v[k] * wy, wx, *r);
                     }
                 } else {
-                    int ax = c0 - md.x; ax += ax < 0 ? L : 0;
+                    int ax = c0 - (rec.x >> 16); ax += ax < 0 ? L : 0;
                     const float wx = ps[ax];
-                    float* cellp = tile + st.x + ax;
+                    float* cellp = tile + (rec.x & 0xffff) + ax;
 #pragma unroll
                     for (int k = 0; k < NCOMP; ++k) {
                         float* r = cellp + (size_t)k * g.tile_elems;
@@ -306,6 +376,12 @@ gather_kernel(const Geom g, const WindowArgs a) {
     __shared__ int s_org[3];
     if (threadIdx.x < 3) s_org[threadIdx.x] = t.org[threadIdx.x];
 
+    StageRegs<DIM> regs;
+    {
+        const long long left = t.p_hi - t.p_lo;
+        stage_prefetch<DIM>(regs, a, t.p_lo, (int)(left < kSubBatch ? left : kSubBatch));
+    }
+
     // stage the padded tile (periodic wrap resolved per quad)
     if (!g.cplx) {
         for_each_quad<DIM>(g, t, [&](int so, long long cell) {
@@ -338,44 +414,77 @@ gather_kernel(const Geom g, const WindowArgs a) {
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // stencil rows (3D) / taps (2D) handled by this lane: r = lane + 32 j
+    constexpr int kRows = LC ? (LC * LC + 31) / 32 : 1;
+    int roff[kRows], ri0[kRows], ri1[kRows];
+    if (LC && DIM >= 2) {
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+            const int r = lane + 32 * j;
+            const int i1 = r / (LC ? LC : 1), i0 = r - i1 * LC;
+            ri0[j] = i0;
+            ri1[j] = r < LC * LC ? i1 : -1;
+            roff[j] = DIM == 3 ? i1 * g.sZ + i0 * g.sY : i1 * g.sY + i0;
+        }
+    }
+
     for (long long p0 = t.p_lo; p0 < t.p_hi; p0 += kSubBatch) {
         const int cnt = (int)((t.p_hi - p0) < kSubBatch ? (t.p_hi - p0) : kSubBatch);
-        stage_points<DIM>(g, a, p0, cnt, s_org, s_psi, s_rec);
+        stage_store<DIM, LC>(regs, g, cnt, s_org, s_psi, s_rec, true);
         __syncthreads();
+        {
+            const long long left = t.p_hi - (p0 + kSubBatch);
+            if (left > 0) stage_prefetch<DIM>(regs, a, p0 + kSubBatch, (int)(left < kSubBatch ? left : kSubBatch));
+        }
         for (int q = warp; q < cnt; q += nwarps) {
-            const int4 st = *reinterpret_cast<const int4*>(s_rec + q * 8);
+            const int4 rec = *reinterpret_cast<const int4*>(s_rec + q * 4);
             const float* ps = s_psi + q * DIM * LP;
             float acc[NCOMP];
 #pragma unroll
             for (int k = 0; k < NCOMP; ++k) acc[k] = 0.f;
             if (DIM == 3) {
-                const float* base = tile + st.z * g.sZ + st.y * g.sY + st.x;
-                float wx[LC ? LC : 1];
+                const float* base = tile + (rec.z & 0xffff) * g.sZ + (rec.y & 0xffff) * g.sY + (rec.x & 0xffff);
                 if (LC) {
+                    constexpr int LQ = LC ? (LC + 3) / 4 : 1;
+                    float wx[LQ * 4];
 #pragma unroll
-                    for (int l = 0; l < LC; ++l) wx[l] = ps[l];
-                }
-                int ay = lane % L, az = lane / L;
-                for (int r = lane; r < L * L; r += 32) {
-                    const float w = ps[2 * LP + az] * ps[LP + ay];  // psi(Z) * psi(Y), then * psi(X)
-                    const float* row = base + az * g.sZ + ay * g.sY;
-#pragma unroll
-                    for (int k = 0; k < NCOMP; ++k) {
-                        const float* rk = row + (size_t)k * g.tile_elems;
-                        float inner = 0.f;
-                        if (LC) {
-#pragma unroll
-                            for (int l = 0; l < LC; ++l) inner = fmaf(w * wx[l], rk[l], inner);
-                        } else {
-                            for (int l = 0; l < L; ++l) inner = fmaf(w * ps[l], rk[l], inner);
-                        }
-                        acc[k] += inner;
+                    for (int l4 = 0; l4 < LQ; ++l4) {
+                        const float4 w4 = reinterpret_cast<const float4*>(ps)[l4];
+                        wx[4 * l4] = w4.x; wx[4 * l4 + 1] = w4.y; wx[4 * l4 + 2] = w4.z; wx[4 * l4 + 3] = w4.w;
                     }
-                    ay += 32;
-                    while (ay >= L) { ay -= L; ++az; }
+#pragma unroll
+                    for (int j = 0; j < kRows; ++j) {
+                        if (ri1[j] >= 0) {
+                            const float w = ps[2 * LP + ri1[j]] * ps[LP + ri0[j]];  // psi(Z) * psi(Y)
+                            const float* row = base + roff[j];
+#pragma unroll
+                            for (int k = 0; k < NCOMP; ++k) {
+                                const float* rk = row + (size_t)k * g.tile_elems;
+                                float inner = 0.f;
+#pragma unroll
+                                for (int l = 0; l < LC; ++l) inner = fmaf(wx[l], rk[l], inner);
+                                acc[k] = fmaf(w, inner, acc[k]);
+                            }
+                        }
+                    }
+                } else {
+                    int ay = lane % L, az = lane / L;
+                    for (int r = lane; r < L * L; r += 32) {
+                        const float w = ps[2 * LP + az] * ps[LP + ay];
+                        const float* row = base + az * g.sZ + ay * g.sY;
+#pragma unroll
+                        for (int k = 0; k < NCOMP; ++k) {
+                            const float* rk = row + (size_t)k * g.tile_elems;
+                            float inner = 0.f;
+                            for (int l = 0; l < L; ++l) inner = fmaf(ps[l], rk[l], inner);
+                            acc[k] = fmaf(w, inner, acc[k]);
+                        }
+                        ay += 32;
+                        while (ay >= L) { ay -= L; ++az; }
+                    }
                 }
             } else if (DIM == 2) {
-                const float* base = tile + st.y * g.sY + st.x;
+                const float* base = tile + (rec.y & 0xffff) * g.sY + (rec.x & 0xffff);
                 int ax = lane % L, ay = lane / L;
                 for (int r = lane; r < L * L; r += 32) {
                     const float w = ps[LP + ay] * ps[ax];
@@ -389,7 +498,7 @@ gather_kernel(const Geom g, const WindowArgs a) {
                 if (lane < L) {
                     const float w = ps[lane];
 #pragma unroll
-                    for (int k = 0; k < NCOMP; ++k) acc[k] = w * tile[(size_t)k * g.tile_elems + st.x + lane];
+                    for (int k = 0; k < NCOMP; ++k) acc[k] = w * tile[(size_t)k * g.tile_elems + (rec.x & 0xffff) + lane];
                 }
             }
 #pragma unroll
@@ -398,7 +507,7 @@ gather_kernel(const Geom g, const WindowArgs a) {
                 for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
             }
             if (lane == 0) {
-                float* dst = a.yout + (size_t)(uint32_t)st.w * g.K + a.k0;
+                float* dst = a.yout + (size_t)(uint32_t)rec.w * g.K + a.k0;
 #pragma unroll
                 for (int k = 0; k < NCOMP; ++k)
                     if (a.k0 + k < g.K) dst[k] = acc[k];
