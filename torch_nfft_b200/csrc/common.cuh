@@ -83,6 +83,7 @@ struct Geom {
     int ncomp;           // components handled per kernel pass (1,2,4,8)
     int pmax;            // max points per work item
     int spread_threads;  // block size of the spread kernel
+    int use_reg;         // 1: register-stencil kernels (window_reg.cuh), 0: team kernels (window.cuh)
     float inv_b, inv_sqrt_b_pi, c_hat;
 };
 

@@ -9,6 +9,8 @@
 #include "sort.cuh"
 #include "spectral.cuh"
 #include "window.cuh"
+#include "window_reg.cuh"
+#include <stdlib.h>
 
 #include <initializer_list>
 #include <map>
@@ -158,6 +160,10 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     const int maxc = d == 3 ? 2 : 8;
     while (ncomp * 2 <= g.K && ncomp * 2 <= maxc) ncomp *= 2;
     if (cplx && ncomp < 2) ncomp = 2;
+    // register-stencil kernels: 3D, m = 4, real grid, one component per pass
+    static const bool no_reg = getenv("NFFTB200_NO_REG") != nullptr;
+    g.use_reg = (d == 3 && m == 4 && !cplx && !no_reg) ? 1 : 0;
+    if (g.use_reg) ncomp = 1;
     g.ncomp = ncomp;
     int T[3] = {1, 1, 1};
     if (d == 1) {
@@ -193,6 +199,7 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
 
     long long pm = n_points / (148 * 8);
     g.pmax = (int)(pm < 256 ? 256 : (pm > 2048 ? 2048 : pm));
+    if (g.use_reg) g.pmax = kRegMaxPts;
     int threads = (team + 31) / 32 * 32;
     g.spread_threads = threads < 64 ? 64 : threads;
     return NFFTB200_OK;
@@ -245,6 +252,19 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
     a.chunk_start = sp.chunk_start;
     a.items = sp.items;
     a.nbins = sp.nbins;
+    if (g.use_reg) {
+        // supercell 4 x 4 x 2 cells: register block 13 x 13 x 11, 5 rows of 13 accumulators per lane
+        WindowKernel kern = spread ? spread_reg_kernel<10, 4, 4, 2> : gather_reg_kernel<10, 4, 4, 2>;
+        const int nsc = ((g.T[0] + 3) / 4) * ((g.T[1] + 3) / 4) * ((g.T[2] + 1) / 2);
+        const size_t smem = reg_smem_bytes(g, nsc);
+        if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
+        NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int k0 = 0; k0 < g.K; ++k0) {
+            a.k0 = k0;
+            NF_LAUNCH(kern, (unsigned)sp.max_items, kRegThreads, smem, st, g, a);
+        }
+        return NFFTB200_OK;
+    }
     // components are processed in passes of <= g.ncomp (real: channels, complex: re/im pairs)
     int ncomp = g.ncomp;
     for (int k0 = 0; k0 < g.K; k0 += ncomp) {
@@ -541,7 +561,7 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
     int v[20] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
-                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads};
+                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.use_reg ? -g.spread_threads : g.spread_threads};
     for (int i = 0; i < 20; ++i) out[i] = v[i];
     return NFFTB200_OK;
 }

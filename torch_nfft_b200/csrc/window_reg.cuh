@@ -1,0 +1,386 @@
+// Register-stencil window kernels (3D): the tap loop runs entirely in registers.
+//
+// The team kernels of window.cuh pay one shared-memory read-modify-write (spread) or read
+// (gather) per window tap, which makes them LSU-bound (ncu: l1tex data-pipe wavefronts ~89 %).
+// Here the chunk's points are first bucketed (in shared memory) by "supercell" = SX x SY x SZ
+// oversampled cells, ordered as columns along Z.  One warp sweeps a column of supercells bottom
+// to top and keeps the (L+SX-1) x (L+SY-1) x (L+SZ-1) block of grid cells its current supercell
+// touches in registers: lane <-> (x, y) positions of the block, WZ consecutive z cells per
+// position.  Each point costs one FFMA per block cell with its zero-padded, shifted tap vectors;
+// the shared-memory tile is touched only when the sweep advances (SZ finished planes are added
+// out / SZ new planes are loaded, the rest of the block slides inside the register file).
+//
+// Products are formed as ((x * psi_y) * psi_x) * psi_z (spread) and (psi_y * psi_x) * sum_z
+// (gather); the reference multiplies dimension 0 first (spatial_window_operations.cu:146-156,
+// 257-267).  The difference is a rounding of ~6e-8 per tap, far below the 1e-5 parity budget.
+#pragma once
+#include "window.cuh"
+
+namespace nfftb200 {
+
+constexpr int kRegThreads = 256;
+constexpr int kRegWarps = kRegThreads / 32;
+constexpr int kRegMaxPts = 1536;  // points per work item (chunk) held in shared memory
+constexpr int kRegGroup = 4;      // points staged per warp round
+
+template <int LC, int SX, int SY, int SZ>
+struct RegCfg {
+    static constexpr int WX = LC + SX - 1, WY = LC + SY - 1, WZ = LC + SZ - 1;
+    static constexpr int WMAX = WX > WY ? (WX > WZ ? WX : WZ) : (WY > WZ ? WY : WZ);
+    static constexpr int WP = (WMAX + 1 + 3) / 4 * 4;  // window pitch; entry WP-1 is always zero
+    static constexpr int COLS = WX * WY;               // (x, y) positions of the register block
+    static constexpr int CPL = (COLS + 31) / 32;       // positions per lane
+    static constexpr int ZQ = (WZ + 3) / 4;            // float4 loads per z window
+};
+
+inline size_t reg_smem_bytes(const Geom& g, int nsc) {
+    // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
+    return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * kRegGroup * 3 * 16 * 4 +
+           (size_t)(2 * nsc + 4) * 4 + (size_t)kRegMaxPts + 64;
+}
+
+// Loads the chunk's points, buckets them by supercell (column-major: z fastest) and leaves them in
+// s_pts as (pos0, pos1, pos2, w), w = x value (spread) or original index (gather), together with
+// the cell offsets inside the supercell s_off = ox | oy << 2 | oz << 4.
+template <int SX, int SY, int SZ, bool SPREAD>
+__device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a, const TileCtx& t, int cnt,
+                                              int nsx, int nsy, int nsz, float4* s_pts, unsigned char* s_off,
+                                              int* s_start, int* s_cur) {
+    constexpr int kPer = (kRegMaxPts + kRegThreads - 1) / kRegThreads;
+    const int nsc = nsx * nsy * nsz;
+    float4 pt[kPer];
+    int sc[kPer];
+    // tile-local cell 0 in wrapped grid coordinates
+    const int lo0 = t.org[0] + g.org[0], lo1 = t.org[1] + g.org[1], lo2 = t.org[2] + g.org[2];
+    const float Mf = (float)g.M;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int e = threadIdx.x + k * kRegThreads;
+        sc[k] = -1;
+        if (e < cnt) {
+            const uint32_t i = a.perm[t.p_lo + e];
+            const float p0 = a.pos[(size_t)i * 3 + 0], p1 = a.pos[(size_t)i * 3 + 1], p2 = a.pos[(size_t)i * 3 + 2];
+            float w;
+            if (SPREAD) w = a.xin[(size_t)i * g.K + a.k0];
+            else w = __int_as_float((int)i);
+            pt[k] = make_float4(p0, p1, p2, w);
+            const int cz = wrap_mod((int)floorf(p0 * Mf), g.M) - lo2;  // API dim 0 = slot Z
+            const int cy = wrap_mod((int)floorf(p1 * Mf), g.M) - lo1;
+            const int cx = wrap_mod((int)floorf(p2 * Mf), g.M) - lo0;
+            const int bx = cx / SX, by = cy / SY, bz = cz / SZ;
+            sc[k] = ((by * nsx + bx) * nsz + bz) | ((cx - bx * SX) | (cy - by * SY) << 2 | (cz - bz * SZ) << 4) << 24;
+            atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the counts by warp 0
+    if (threadIdx.x < 32) {
+        int running = 0;
+        for (int base = 0; base < nsc; base += 32) {
+            const int idx = base + (int)threadIdx.x;
+            const int v = idx < nsc ? s_cur[idx] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += n;
+            }
+            if (idx < nsc) s_start[idx] = running + incl - v;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (threadIdx.x == 0) s_start[nsc] = running;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = s_start[i];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if (sc[k] >= 0) {
+            const int dst = atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
+            s_pts[dst] = pt[k];
+            s_off[dst] = (unsigned char)((unsigned)sc[k] >> 24);
+        }
+    }
+    __syncthreads();
+}
+
+// Phase A of a warp round: lanes 0 .. 3*LC-1 evaluate one window tap each for up to kRegGroup points
+// and store it at its shifted position inside the point's zero-initialised windows
+// (window order in shared memory: X, Y, Z).
+template <int LC, int WP>
+__device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
+                                              int npts, float* win, int lane, bool pow2) {
+    constexpr int kQuads = kRegGroup * 3 * WP / 4;
+#pragma unroll
+    for (int k = 0; k < (kQuads + 31) / 32; ++k) {
+        const int qd = lane + 32 * k;
+        if (qd < kQuads) reinterpret_cast<float4*>(win)[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if (lane < 3 * LC) {
+        const int api = lane / LC, l = lane - api * LC;  // API dim 0,1,2 <-> slot Z,Y,X
+        const int slot = 2 - api;
+        const float Mf = (float)g.M;
+        const float ml = (float)(g.m - l);
+#pragma unroll
+        for (int gp = 0; gp < kRegGroup; ++gp) {
+            if (gp < npts) {
+                const float4 pt = s_pts[base + gp];
+                const int off = (s_off[base + gp] >> (2 * slot)) & 3;
+                const float p = api == 0 ? pt.x : (api == 1 ? pt.y : pt.z);
+                const float pm = p * Mf;
+                const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
+                float tt;
+                if (pow2) {
+                    // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or
+                    // correctly rounded, i.e. identical to the reference's double evaluation
+                    tt = (pm - fl) + ml;
+                } else {
+                    const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
+                    tt = (float)(bd - (double)l);
+                }
+                win[(gp * 3 + slot) * WP + off + l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ======================================================================================
+// spread
+// ======================================================================================
+template <int LC, int SX, int SY, int SZ>
+__global__ void __launch_bounds__(kRegThreads, 2)
+spread_reg_kernel(const Geom g, const WindowArgs a) {
+    using Cfg = RegCfg<LC, SX, SY, SZ>;
+    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, WP = Cfg::WP, CPL = Cfg::CPL;
+    extern __shared__ __align__(16) float smem[];
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+
+    const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
+    const int nsc = nsx * nsy * nsz;
+    float* tile = smem;
+    float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
+    float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
+    int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * kRegGroup * 3 * WP);
+    int* s_cur = s_start + nsc + 2;
+    unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
+    __shared__ int s_next;
+
+    for (int i = threadIdx.x; i < g.tile_elems; i += kRegThreads) tile[i] = 0.f;
+    for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    const int cnt = (int)(t.p_hi - t.p_lo);
+    bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* win = s_win + warp * (kRegGroup * 3 * WP);
+    const int padx = g.org[0] - g.m;
+    const bool pow2 = (g.M & (g.M - 1)) == 0;
+    // (x, y) positions of the register block owned by this lane: c = lane + 32 q -> (c % WX, c / WX)
+    int iq[CPL], jq[CPL], coff[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        const bool ok = c < Cfg::COLS;
+        iq[q] = ok ? c % WX : WP - 1;  // WP-1: an always-zero window entry -> weight 0
+        jq[q] = ok ? c / WX : WP - 1;
+        coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
+    }
+
+    // columns of supercells are handed out dynamically, one per warp
+    for (;;) {
+        int col = 0;
+        if (lane == 0) col = atomicAdd(&s_next, 1);
+        col = __shfl_sync(0xffffffffu, col, 0);
+        if (col >= nsx * nsy) break;
+        const int c0 = col * nsz;
+        if (s_start[c0] == s_start[c0 + nsz]) continue;  // empty column
+        const int scx = col % nsx, scy = col / nsx;
+        float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
+
+        float acc[CPL][WZ];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+#pragma unroll
+            for (int k = 0; k < WZ; ++k) acc[q][k] = 0.f;
+
+        for (int scz = 0; scz < nsz; ++scz) {
+            const int lo = s_start[c0 + scz], hi = s_start[c0 + scz + 1];
+            for (int base = lo; base < hi; base += kRegGroup) {
+                const int npts = hi - base < kRegGroup ? hi - base : kRegGroup;
+                stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
+#pragma unroll
+                for (int gp = 0; gp < kRegGroup; ++gp) {
+                    if (gp < npts) {
+                        const float* wv = win + gp * 3 * WP;
+                        const float xval = s_pts[base + gp].w;
+                        float wz[Cfg::ZQ * 4];
+#pragma unroll
+                        for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                            const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                            wz[4 * l4] = w4.x; wz[4 * l4 + 1] = w4.y; wz[4 * l4 + 2] = w4.z; wz[4 * l4 + 3] = w4.w;
+                        }
+                        float v[CPL];
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[WP + jq[q]]) * wv[iq[q]];
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q)
+#pragma unroll
+                            for (int k = 0; k < WZ; ++k) acc[q][k] = fmaf(v[q], wz[k], acc[q][k]);
+                    }
+                }
+                __syncwarp();
+            }
+            // planes 0 .. SZ-1 of the block are complete: add them out, slide the block up by SZ
+            const bool last = scz == nsz - 1;
+            float* pbase = cbase + (scz * SZ) * g.sZ;
+#pragma unroll
+            for (int k = 0; k < WZ; ++k) {
+                if (k < SZ || last) {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q)
+                        if (lane + 32 * q < Cfg::COLS && acc[q][k] != 0.f) atomicAdd(pbase + k * g.sZ + coff[q], acc[q][k]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+                for (int k = 0; k < WZ; ++k) acc[q][k] = k + SZ < WZ ? acc[q][k + SZ] : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
+    // flush: vector reductions into the global grid; untouched (== 0) quads are skipped
+    for_each_quad<3>(g, t, [&](int so, long long cell) {
+        const float* s = tile + so;
+        const float4 val = make_float4(s[0], s[1], s[2], s[3]);
+        if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) {
+            float4* dst = reinterpret_cast<float4*>(a.grid + grid_plane(g, t.b, a.k0) + cell);
+            atomicAdd(dst, val);
+        }
+    });
+}
+
+// ======================================================================================
+// gather
+// ======================================================================================
+template <int LC, int SX, int SY, int SZ>
+__global__ void __launch_bounds__(kRegThreads, 2)
+gather_reg_kernel(const Geom g, const WindowArgs a) {
+    using Cfg = RegCfg<LC, SX, SY, SZ>;
+    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, WP = Cfg::WP, CPL = Cfg::CPL;
+    extern __shared__ __align__(16) float smem[];
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+
+    const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
+    const int nsc = nsx * nsy * nsz;
+    float* tile = smem;
+    float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
+    float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
+    int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * kRegGroup * 3 * WP);
+    int* s_cur = s_start + nsc + 2;
+    unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
+    __shared__ int s_next;
+
+    for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
+    if (threadIdx.x == 0) s_next = 0;
+    // stage the padded tile (periodic wrap resolved per quad)
+    for_each_quad<3>(g, t, [&](int so, long long cell) {
+        const float4 val = __ldg(reinterpret_cast<const float4*>(a.grid + grid_plane(g, t.b, a.k0) + cell));
+        float* s = tile + so;
+        s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
+    });
+    __syncthreads();
+    const int cnt = (int)(t.p_hi - t.p_lo);
+    bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* win = s_win + warp * (kRegGroup * 3 * WP);
+    const int padx = g.org[0] - g.m;
+    const bool pow2 = (g.M & (g.M - 1)) == 0;
+    int iq[CPL], jq[CPL], coff[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        const bool ok = c < Cfg::COLS;
+        iq[q] = ok ? c % WX : WP - 1;
+        jq[q] = ok ? c / WX : WP - 1;
+        coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
+    }
+
+    for (;;) {
+        int col = 0;
+        if (lane == 0) col = atomicAdd(&s_next, 1);
+        col = __shfl_sync(0xffffffffu, col, 0);
+        if (col >= nsx * nsy) break;
+        const int c0 = col * nsz;
+        if (s_start[c0] == s_start[c0 + nsz]) continue;
+        const int scx = col % nsx, scy = col / nsx;
+        const float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
+
+        // register block: planes [scz*SZ, scz*SZ + WZ) of the column; loaded for scz = 0, then slid
+        float blk[CPL][WZ];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+#pragma unroll
+            for (int k = 0; k < WZ; ++k) blk[q][k] = k >= SZ ? cbase[(k - SZ) * g.sZ + coff[q]] : 0.f;
+
+        for (int scz = 0; scz < nsz; ++scz) {
+            // slide down by SZ and load the SZ new top planes
+            const float* pbase = cbase + (scz * SZ) * g.sZ;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+                for (int k = 0; k < WZ; ++k)
+                    blk[q][k] = k + SZ < WZ ? blk[q][k + SZ] : pbase[k * g.sZ + coff[q]];
+            }
+            const int lo = s_start[c0 + scz], hi = s_start[c0 + scz + 1];
+            for (int base = lo; base < hi; base += kRegGroup) {
+                const int npts = hi - base < kRegGroup ? hi - base : kRegGroup;
+                stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
+                float part[kRegGroup];
+#pragma unroll
+                for (int gp = 0; gp < kRegGroup; ++gp) {
+                    part[gp] = 0.f;
+                    if (gp < npts) {
+                        const float* wv = win + gp * 3 * WP;
+                        float wz[Cfg::ZQ * 4];
+#pragma unroll
+                        for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                            const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                            wz[4 * l4] = w4.x; wz[4 * l4 + 1] = w4.y; wz[4 * l4 + 2] = w4.z; wz[4 * l4 + 3] = w4.w;
+                        }
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) {
+                            const float w = wv[WP + jq[q]] * wv[iq[q]];  // psi(Y) * psi(X)
+                            float inner = 0.f;
+#pragma unroll
+                            for (int k = 0; k < WZ; ++k) inner = fmaf(wz[k], blk[q][k], inner);
+                            part[gp] = fmaf(w, inner, part[gp]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int gp = 0; gp < kRegGroup; ++gp) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part[gp] += __shfl_xor_sync(0xffffffffu, part[gp], o);
+                }
+                if (lane < npts) {
+                    float v = part[0];
+#pragma unroll
+                    for (int gp = 1; gp < kRegGroup; ++gp) v = lane == gp ? part[gp] : v;
+                    const uint32_t i = (uint32_t)__float_as_int(s_pts[base + lane].w);
+                    a.yout[(size_t)i * g.K + a.k0] = v;
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+}  // namespace nfftb200
