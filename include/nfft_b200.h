@@ -56,6 +56,9 @@ extern "C" {
 #define NFFTB200_Y_REAL 2         /* adjoint/forward: write only the real part (real_output) */
 #define NFFTB200_COEFFS_COMPLEX 4 /* fastsum: coeffs are complex64                           */
 #define NFFTB200_SYMMETRIC 8      /* fastsum: targets are the sources (reuse the sort)       */
+#define NFFTB200_PRESORTED 16     /* adjoint/forward: the workspace still holds the sort of  */
+                                  /* exactly these points (same pos, batch, d, N, m, B, C    */
+                                  /* and value type) from the previous call on it            */
 
 int nfftb200_version(void);
 const char* nfftb200_last_error(void);

@@ -352,3 +352,33 @@ def test_full_size_properties(name, clustered):
     assert float((lhs - rhs).abs() / lhs.abs()) < 1e-5
     fr = T.nfft_forward(yh, pos, batch, m, real_output=True, batch_size=B)
     assert float(torch.linalg.vector_norm(fr - fy.real) / torch.linalg.vector_norm(fr)) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# reuse of the point sort between transforms of the same point set
+# ---------------------------------------------------------------------------------------------
+def test_sort_reuse_between_adjoint_and_forward():
+    from torch_nfft_b200 import nfft as nfft_mod
+    rng = np.random.default_rng(11)
+    pos, batch = make_points(rng, 3, 2, 3000)
+    x = make_values(rng, (pos.shape[0], 1), False)
+    tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
+    T.clear_caches()
+    before = _lib.launch_count()
+    y = T.nfft_adjoint(tx, tp, tb, 32, 4)
+    first = _lib.launch_count() - before
+    f = T.nfft_forward(y, tp, tb, 4, real_output=True)  # same points, same tiling: no second sort
+    second = _lib.launch_count() - before - first
+    assert second < first - 8, (first, second)
+    ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
+    assert O.rel_l2(y.cpu().numpy(), ref_y) < TOL
+    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, 4, real_output=True)) < TOL
+    # an in-place change of the points invalidates the remembered sort
+    tp.mul_(0.5)
+    f2 = T.nfft_forward(y, tp, tb, 4, real_output=True)
+    assert O.rel_l2(f2.cpu().numpy(), O.nfft_forward(ref_y, (pos * 0.5).astype(np.float32), batch, 4, real_output=True)) < TOL
+    # a different tensor with the same shape is never taken for the remembered one
+    tp2 = cuda(pos)
+    f3 = T.nfft_forward(y, tp2, tb, 4, real_output=True)
+    assert O.rel_l2(f3.cpu().numpy(), f.cpu().numpy()) < 1e-6
+    assert nfft_mod._PLAN_REUSE

@@ -22,15 +22,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(_SRC_DIR, d)) > t for d in _DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if it is missing or older than its sources."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compile the CUDA library if it is missing or older than its sources.
+    `defines` / `out` build an experimental variant next to the default library."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("torch_nfft_b200: nvcc not found; cannot build libnfft_b200.so")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + _SOURCES + ["-lcufft"]
+           "-shared", "-Xcompiler", "-fPIC", "-o", out or LIB_PATH] + ["-D" + d for d in defines] + _SOURCES + ["-lcufft"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=_SRC_DIR, capture_output=True, text=True)
@@ -38,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("torch_nfft_b200: nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":

@@ -7,10 +7,13 @@ import ctypes
 import os
 import threading
 
-from ._build import LIB_PATH
+from ._build import LIB_PATH as _DEFAULT_LIB_PATH
+
+# development aid: NFFTB200_LIB selects an alternative build of the same library (A/B experiments)
+LIB_PATH = os.environ.get("NFFTB200_LIB", _DEFAULT_LIB_PATH)
 
 OP_ADJOINT, OP_FORWARD, OP_FASTSUM, OP_SPREAD, OP_GATHER, OP_SORT, OP_SPECTRAL = range(7)
-X_COMPLEX, Y_REAL, COEFFS_COMPLEX, SYMMETRIC = 1, 2, 4, 8
+X_COMPLEX, Y_REAL, COEFFS_COMPLEX, SYMMETRIC, PRESORTED = 1, 2, 4, 8, 16
 
 _lock = threading.Lock()
 _lib = None

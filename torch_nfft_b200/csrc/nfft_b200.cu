@@ -348,13 +348,15 @@ static unsigned blocks_for(long long total, int threads = 256) { return (unsigne
 // stage implementations
 // ----------------------------------------------------------------------------------------
 static int do_spread(const Geom& g, const float* pos, const float* x, const int64_t* batch, float* grid, long long n,
-                     char* sort_ws, SortPlan* sp_out, cudaStream_t st) {
+                     char* sort_ws, SortPlan* sp_out, cudaStream_t st, bool presorted = false) {
     {
         ProfScope ps(ST_MEMSET, st);
         NF_CUDA(cudaMemsetAsync(grid, 0, (size_t)g.B * g.C * g.Md * (g.cplx ? 8 : 4), st));
     }
     SortPlan sp{};
-    {
+    if (presorted) {
+        sort_plan_pointers(n, g, sort_ws, &sp);
+    } else {
         ProfScope ps(ST_SORT, st);
         NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
     }
@@ -369,11 +371,13 @@ static int do_spread(const Geom& g, const float* pos, const float* x, const int6
 }
 
 static int do_gather(const Geom& g, const float* pos, const int64_t* batch, const float* grid, float* y, long long n,
-                     char* sort_ws, const SortPlan* presorted, cudaStream_t st) {
+                     char* sort_ws, const SortPlan* presorted, cudaStream_t st, bool presorted_ws = false) {
     if (n == 0) return NFFTB200_OK;
     SortPlan sp{};
     if (presorted) {
         sp = *presorted;
+    } else if (presorted_ws) {
+        sort_plan_pointers(n, g, sort_ws, &sp);
     } else {
         ProfScope ps(ST_SORT, st);
         NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
@@ -642,7 +646,7 @@ int nfftb200_adjoint(const float* pos, const void* x, const int64_t* batch, void
     char* ws = align_ptr(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     float* grid = (float*)(ws + w.grid);
-    NF_TRY(do_spread(g, pos, (const float*)x, batch, grid, n, ws + w.sort, nullptr, st));
+    NF_TRY(do_spread(g, pos, (const float*)x, batch, grid, n, ws + w.sort, nullptr, st, flags & NFFTB200_PRESORTED));
     return do_adjoint_finish(g, grid, (float*)y, yr, (float2*)(ws + w.spec), st);
 }
 
@@ -659,7 +663,7 @@ int nfftb200_forward(const float* pos, const void* xhat, const int64_t* batch, v
     cudaStream_t st = (cudaStream_t)stream;
     float* grid = (float*)(ws + w.grid);
     NF_TRY(do_forward_begin(g, (const float*)xhat, !xc, yr, grid, (float2*)(ws + w.spec), st));
-    return do_gather(g, pos, batch, grid, (float*)y, n, ws + w.sort, nullptr, st);
+    return do_gather(g, pos, batch, grid, (float*)y, n, ws + w.sort, nullptr, st, flags & NFFTB200_PRESORTED);
 }
 
 int nfftb200_fastsum(const float* sources, const float* targets, const void* x, const void* coeffs,

@@ -286,17 +286,35 @@ inline SortLayout sort_layout(long long n, const Geom& g) {
     return L;
 }
 
+// Pointers of the sort result inside `ws` (a pure function of n and the geometry, so a caller that
+// kept the workspace can reuse a previous sort of the same points: NFFTB200_PRESORTED).
+inline void sort_plan_pointers(long long n, const Geom& g, char* ws, SortPlan* plan) {
+    const SortLayout L = sort_layout(n, g);
+    int bits = 0;
+    while (bits < 32 && (1ll << bits) < L.nbins) ++bits;
+    const int passes = (bits + 7) / 8;
+    uint32_t* ibuf[2] = {(uint32_t*)(ws + L.idxA), (uint32_t*)(ws + L.idxB)};
+    plan->keys = (uint32_t*)(ws + L.keys0);
+    plan->perm = passes == 0 ? ibuf[0] : ibuf[(passes - 1) & 1];
+    plan->bin_start = (uint32_t*)(ws + L.bin_start);
+    plan->chunk_start = (uint32_t*)(ws + L.chunk_start);
+    plan->items = (int2*)(ws + L.items);
+    plan->nbins = L.nbins;
+    plan->max_items = L.max_items;
+}
+
 // Bins n points; on return plan.* point into `ws` (which must hold sort_layout(n,g).total bytes).
 inline int sort_points(const float* pos, const int64_t* batch, long long n, const Geom& g, char* ws,
                        SortPlan* plan, cudaStream_t st) {
     const SortLayout L = sort_layout(n, g);
-    uint32_t* keys0 = (uint32_t*)(ws + L.keys0);
+    sort_plan_pointers(n, g, ws, plan);
+    uint32_t* keys0 = plan->keys;
     uint32_t* kbuf[2] = {(uint32_t*)(ws + L.keysA), (uint32_t*)(ws + L.keysB)};
     uint32_t* ibuf[2] = {(uint32_t*)(ws + L.idxA), (uint32_t*)(ws + L.idxB)};
     uint32_t* bin_count = (uint32_t*)(ws + L.bin_count);
-    uint32_t* bin_start = (uint32_t*)(ws + L.bin_start);
+    uint32_t* bin_start = plan->bin_start;
     uint32_t* nch = (uint32_t*)(ws + L.nch);
-    uint32_t* chunk_start = (uint32_t*)(ws + L.chunk_start);
+    uint32_t* chunk_start = plan->chunk_start;
     uint32_t* table = (uint32_t*)(ws + L.table);
     uint32_t* scan = (uint32_t*)(ws + L.scan);
 
@@ -307,8 +325,7 @@ inline int sort_points(const float* pos, const int64_t* batch, long long n, cons
     NF_TRY(scan_exclusive(bin_count, bin_start, L.nbins, scan, st));
     NF_LAUNCH(chunk_count_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, bin_start, L.nbins, g.pmax, nch);
     NF_TRY(scan_exclusive(nch, chunk_start, L.nbins, scan, st));
-    NF_LAUNCH(fill_items_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, chunk_start, L.nbins,
-              (int2*)(ws + L.items));
+    NF_LAUNCH(fill_items_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, chunk_start, L.nbins, plan->items);
 
     // stable LSD radix sort of (key, index) over the key bits that can be set
     int bits = 0;
@@ -316,7 +333,6 @@ inline int sort_points(const float* pos, const int64_t* batch, long long n, cons
     const int passes = (bits + 7) / 8;
     const uint32_t* kin = keys0;
     const uint32_t* iin = nullptr;  // identity payload on the first pass
-    uint32_t* perm = ibuf[0];
     if (n > 0) {
         if (passes == 0) {
             NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, ibuf[0], n);
@@ -331,16 +347,8 @@ inline int sort_points(const float* pos, const int64_t* batch, long long n, cons
                       table, (int)L.nblocks);
             kin = kout;
             iin = iout;
-            perm = iout;
         }
     }
-    plan->keys = keys0;
-    plan->perm = perm;
-    plan->bin_start = bin_start;
-    plan->chunk_start = chunk_start;
-    plan->items = (int2*)(ws + L.items);
-    plan->nbins = L.nbins;
-    plan->max_items = L.max_items;
     return NFFTB200_OK;
 }
 

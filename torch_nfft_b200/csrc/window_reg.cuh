@@ -21,7 +21,16 @@ namespace nfftb200 {
 constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
 constexpr int kRegMaxPts = 1536;  // points per work item (chunk) held in shared memory
-constexpr int kRegGroup = 4;      // points staged per warp round
+#ifndef NFFT_REG_GROUP
+#define NFFT_REG_GROUP 8
+#endif
+#ifndef NFFT_REG_FFMA2
+#define NFFT_REG_FFMA2 1
+#endif
+#ifndef NFFT_REG_PTLOOP
+#define NFFT_REG_PTLOOP 1
+#endif
+constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round
 
 template <int LC, int SX, int SY, int SZ>
 struct RegCfg {
@@ -31,7 +40,18 @@ struct RegCfg {
     static constexpr int COLS = WX * WY;               // (x, y) positions of the register block
     static constexpr int CPL = (COLS + 31) / 32;       // positions per lane
     static constexpr int ZQ = (WZ + 3) / 4;            // float4 loads per z window
+    static constexpr int ZP = ZQ * 2;                  // float2 (packed fp32x2) accumulators per position
+    static_assert(SZ % 2 == 0, "the block slides by whole float2 pairs");
 };
+
+// packed fp32x2 FMA (sm_100 FFMA2): d = a * b + c on both halves
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#if NFFT_REG_FFMA2
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
 
 inline size_t reg_smem_bytes(const Geom& g, int nsc) {
     // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
@@ -122,25 +142,27 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
         const int slot = 2 - api;
         const float Mf = (float)g.M;
         const float ml = (float)(g.m - l);
+        const float* pcoord = reinterpret_cast<const float*>(s_pts + base) + api;
+        float* wdst = win + slot * WP + l;
+        // kRegGroup independent dependency chains (unrolled): the expf latency of one point hides
+        // behind the others.  Slots beyond npts compute on stale data and are not stored.
 #pragma unroll
         for (int gp = 0; gp < kRegGroup; ++gp) {
-            if (gp < npts) {
-                const float4 pt = s_pts[base + gp];
-                const int off = (s_off[base + gp] >> (2 * slot)) & 3;
-                const float p = api == 0 ? pt.x : (api == 1 ? pt.y : pt.z);
-                const float pm = p * Mf;
-                const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
-                float tt;
-                if (pow2) {
-                    // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or
-                    // correctly rounded, i.e. identical to the reference's double evaluation
-                    tt = (pm - fl) + ml;
-                } else {
-                    const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
-                    tt = (float)(bd - (double)l);
-                }
-                win[(gp * 3 + slot) * WP + off + l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+            const int off = (s_off[base + gp] >> (2 * slot)) & 3;
+            const float p = pcoord[4 * gp];
+            const float pm = p * Mf;
+            const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
+            float tt;
+            if (pow2) {
+                // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or
+                // correctly rounded, i.e. identical to the reference's double evaluation
+                tt = (pm - fl) + ml;
+            } else {
+                const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
+                tt = (float)(bd - (double)l);
             }
+            const float val = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+            if (gp < npts) wdst[gp * 3 * WP + off] = val;
         }
     }
     __syncwarp();
@@ -153,7 +175,7 @@ template <int LC, int SX, int SY, int SZ>
 __global__ void __launch_bounds__(kRegThreads, 2)
 spread_reg_kernel(const Geom g, const WindowArgs a) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
-    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, WP = Cfg::WP, CPL = Cfg::CPL;
+    constexpr int WX = Cfg::WX, WP = Cfg::WP, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
@@ -167,6 +189,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     int* s_cur = s_start + nsc + 2;
     unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
     __shared__ int s_next;
+    __shared__ int s_lock[64];  // one lock per pair of tile planes
+    if (threadIdx.x < 64) s_lock[threadIdx.x] = 0;
 
     for (int i = threadIdx.x; i < g.tile_elems; i += kRegThreads) tile[i] = 0.f;
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
@@ -179,15 +203,14 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     float* win = s_win + warp * (kRegGroup * 3 * WP);
     const int padx = g.org[0] - g.m;
     const bool pow2 = (g.M & (g.M - 1)) == 0;
-    // (x, y) positions of the register block owned by this lane: c = lane + 32 q -> (c % WX, c / WX)
-    int iq[CPL], jq[CPL], coff[CPL];
+    // (x, y) positions of the register block owned by this lane: c = lane + 32 q -> (c % WX, c / WX),
+    // packed as window indices  i | (WP + j) << 8  (invalid positions read the always-zero entry WP-1)
+    int ij[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
         const bool ok = c < Cfg::COLS;
-        iq[q] = ok ? c % WX : WP - 1;  // WP-1: an always-zero window entry -> weight 0
-        jq[q] = ok ? c / WX : WP - 1;
-        coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
+        ij[q] = ok ? (c % WX) | (WP + c / WX) << 8 : (WP - 1) | (2 * WP - 1) << 8;
     }
 
     // columns of supercells are handed out dynamically, one per warp
@@ -201,54 +224,86 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         const int scx = col % nsx, scy = col / nsx;
         float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
 
-        float acc[CPL][WZ];
+        float2 acc[CPL][ZP];  // acc[q][kp] = block cells (k = 2 kp, 2 kp + 1) at position q
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
-            for (int k = 0; k < WZ; ++k) acc[q][k] = 0.f;
+            for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = make_float2(0.f, 0.f);
 
         for (int scz = 0; scz < nsz; ++scz) {
             const int lo = s_start[c0 + scz], hi = s_start[c0 + scz + 1];
             for (int base = lo; base < hi; base += kRegGroup) {
                 const int npts = hi - base < kRegGroup ? hi - base : kRegGroup;
                 stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
+                const float* wv = win;
+#if NFFT_REG_PTLOOP
+                for (int gp = 0; gp < npts; ++gp, wv += 3 * WP) {
+#else
 #pragma unroll
-                for (int gp = 0; gp < kRegGroup; ++gp) {
-                    if (gp < npts) {
-                        const float* wv = win + gp * 3 * WP;
-                        const float xval = s_pts[base + gp].w;
-                        float wz[Cfg::ZQ * 4];
+                for (int gp = 0; gp < kRegGroup; ++gp, wv += 3 * WP) {
+                    if (gp >= npts) continue;
+#endif
+                    const float xval = s_pts[base + gp].w;
+                    float2 wz[ZP];
 #pragma unroll
-                        for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                            const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
-                            wz[4 * l4] = w4.x; wz[4 * l4 + 1] = w4.y; wz[4 * l4 + 2] = w4.z; wz[4 * l4 + 3] = w4.w;
-                        }
-                        float v[CPL];
+                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                        const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                        wz[2 * l4] = make_float2(w4.x, w4.y);
+                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
+                    }
+                    float v[CPL];
 #pragma unroll
-                        for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[WP + jq[q]]) * wv[iq[q]];
+                    for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[ij[q] >> 8]) * wv[ij[q] & 0xff];
 #pragma unroll
-                        for (int q = 0; q < CPL; ++q)
+                    for (int q = 0; q < CPL; ++q) {
+                        const float2 vv = make_float2(v[q], v[q]);
 #pragma unroll
-                            for (int k = 0; k < WZ; ++k) acc[q][k] = fmaf(v[q], wz[k], acc[q][k]);
+                        for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
                     }
                 }
                 __syncwarp();
             }
-            // planes 0 .. SZ-1 of the block are complete: add them out, slide the block up by SZ
+            // planes 0 .. SZ-1 of the block are complete: add them out, slide the block up by SZ.
+            // Other warps' blocks overlap this one in x/y, so each pair of tile planes is guarded by
+            // a shared-memory lock; inside it the update is a plain pipelined LDS / FADD / STS
+            // (a shared-memory float atomicAdd is a CAS loop per element on sm_100a).
             const bool last = scz == nsz - 1;
-            float* pbase = cbase + (scz * SZ) * g.sZ;
+            const int zlim = g.P[2] - scz * SZ;  // planes of the padded tile above the block origin
 #pragma unroll
-            for (int k = 0; k < WZ; ++k) {
-                if (k < SZ || last) {
+            for (int kp = 0; kp < ZP; ++kp) {
+                if ((kp < SP || last) && 2 * kp < zlim) {
+                    float* pbase = cbase + (scz * SZ + 2 * kp) * g.sZ;
+                    const bool two = 2 * kp + 1 < zlim;
+                    int* lk = s_lock + scz * SP + kp;
+                    if (lane == 0) {
+                        while (atomicCAS(lk, 0, 1) != 0) __nanosleep(32);
+                    }
+                    __syncwarp();
+                    float2 cur[CPL];
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q)
-                        if (lane + 32 * q < Cfg::COLS && acc[q][k] != 0.f) atomicAdd(pbase + k * g.sZ + coff[q], acc[q][k]);
+                    for (int q = 0; q < CPL; ++q) {
+                        const float* src = pbase + ((ij[q] >> 8) - WP) * g.sY + (ij[q] & 0xff);
+                        const bool ok = lane + 32 * q < Cfg::COLS;
+                        cur[q].x = ok ? src[0] : 0.f;
+                        cur[q].y = ok && two ? src[g.sZ] : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        float* dst = pbase + ((ij[q] >> 8) - WP) * g.sY + (ij[q] & 0xff);
+                        if (lane + 32 * q < Cfg::COLS) {
+                            dst[0] = cur[q].x + acc[q][kp].x;
+                            if (two) dst[g.sZ] = cur[q].y + acc[q][kp].y;
+                        }
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) atomicExch(lk, 0);
                 }
             }
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
 #pragma unroll
-                for (int k = 0; k < WZ; ++k) acc[q][k] = k + SZ < WZ ? acc[q][k + SZ] : 0.f;
+                for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = kp + SP < ZP ? acc[q][kp + SP] : make_float2(0.f, 0.f);
             }
         }
     }
@@ -272,7 +327,7 @@ template <int LC, int SX, int SY, int SZ>
 __global__ void __launch_bounds__(kRegThreads, 2)
 gather_reg_kernel(const Geom g, const WindowArgs a) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
-    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, WP = Cfg::WP, CPL = Cfg::CPL;
+    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, WP = Cfg::WP, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
@@ -303,15 +358,16 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     float* win = s_win + warp * (kRegGroup * 3 * WP);
     const int padx = g.org[0] - g.m;
     const bool pow2 = (g.M & (g.M - 1)) == 0;
-    int iq[CPL], jq[CPL], coff[CPL];
+    int ij[CPL], coff[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
         const bool ok = c < Cfg::COLS;
-        iq[q] = ok ? c % WX : WP - 1;
-        jq[q] = ok ? c / WX : WP - 1;
+        ij[q] = ok ? (c % WX) | (WP + c / WX) << 8 : (WP - 1) | (2 * WP - 1) << 8;
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
+    // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
+    const int zmax = g.P[2] - 1;
 
     for (;;) {
         int col = 0;
@@ -323,21 +379,32 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         const int scx = col % nsx, scy = col / nsx;
         const float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
 
-        // register block: planes [scz*SZ, scz*SZ + WZ) of the column; loaded for scz = 0, then slid
-        float blk[CPL][WZ];
+        // register block: planes [scz*SZ, scz*SZ + 2 ZP) of the column; loaded for scz = 0, then slid
+        float2 blk[CPL][ZP];
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
-            for (int k = 0; k < WZ; ++k) blk[q][k] = k >= SZ ? cbase[(k - SZ) * g.sZ + coff[q]] : 0.f;
+            for (int kp = 0; kp < ZP; ++kp) {
+                // pre-slide position: after the first slide pair kp holds planes 2 kp, 2 kp + 1
+                const int k = 2 * (kp - SP);
+                blk[q][kp] = kp >= SP ? make_float2(cbase[k * g.sZ + coff[q]], cbase[(k + 1) * g.sZ + coff[q]])
+                                      : make_float2(0.f, 0.f);
+            }
 
         for (int scz = 0; scz < nsz; ++scz) {
             // slide down by SZ and load the SZ new top planes
-            const float* pbase = cbase + (scz * SZ) * g.sZ;
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
 #pragma unroll
-                for (int k = 0; k < WZ; ++k)
-                    blk[q][k] = k + SZ < WZ ? blk[q][k + SZ] : pbase[k * g.sZ + coff[q]];
+                for (int kp = 0; kp < ZP; ++kp) {
+                    if (kp + SP < ZP) {
+                        blk[q][kp] = blk[q][kp + SP];
+                    } else {
+                        const int z0 = scz * SZ + 2 * kp;
+                        const int za = z0 < zmax ? z0 : zmax, zb = z0 + 1 < zmax ? z0 + 1 : zmax;
+                        blk[q][kp] = make_float2(cbase[za * g.sZ + coff[q]], cbase[zb * g.sZ + coff[q]]);
+                    }
+                }
             }
             const int lo = s_start[c0 + scz], hi = s_start[c0 + scz + 1];
             for (int base = lo; base < hi; base += kRegGroup) {
@@ -345,24 +412,28 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                 stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
                 float part[kRegGroup];
 #pragma unroll
-                for (int gp = 0; gp < kRegGroup; ++gp) {
-                    part[gp] = 0.f;
+                for (int gp = 0; gp < kRegGroup; ++gp) part[gp] = 0.f;
+                const float* wv = win;
+#pragma unroll
+                for (int gp = 0; gp < kRegGroup; ++gp, wv += 3 * WP) {
                     if (gp < npts) {
-                        const float* wv = win + gp * 3 * WP;
-                        float wz[Cfg::ZQ * 4];
+                        float2 wz[ZP];
 #pragma unroll
                         for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
                             const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
-                            wz[4 * l4] = w4.x; wz[4 * l4 + 1] = w4.y; wz[4 * l4 + 2] = w4.z; wz[4 * l4 + 3] = w4.w;
+                            wz[2 * l4] = make_float2(w4.x, w4.y);
+                            wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
                         }
+                        float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int q = 0; q < CPL; ++q) {
-                            const float w = wv[WP + jq[q]] * wv[iq[q]];  // psi(Y) * psi(X)
-                            float inner = 0.f;
+                            const float w = wv[ij[q] >> 8] * wv[ij[q] & 0xff];  // psi(Y) * psi(X)
+                            float2 inner = make_float2(0.f, 0.f);
 #pragma unroll
-                            for (int k = 0; k < WZ; ++k) inner = fmaf(wz[k], blk[q][k], inner);
-                            part[gp] = fmaf(w, inner, part[gp]);
+                            for (int kp = 0; kp < ZP; ++kp) inner = ffma2(wz[kp], blk[q][kp], inner);
+                            sum = ffma2(make_float2(w, w), inner, sum);
                         }
+                        part[gp] = sum.x + sum.y;
                     }
                 }
 #pragma unroll
@@ -381,6 +452,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
             }
         }
     }
+    (void)WZ;
 }
 
 }  // namespace nfftb200

@@ -15,11 +15,19 @@ Additions over the reference (all optional, defaults reproduce the reference):
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import torch
 
 from . import _lib
 
 _workspaces = {}
+# What the sort region of each workspace currently holds: the adjoint and forward transforms of the
+# same point set (forward + backward of autograd, iterative solvers) then skip the binning pass.
+# The reference recomputes its per-point scratch on every call (core_cuda.cu:188-211, 461-484).
+_sorted_points = {}
+_PLAN_REUSE = os.environ.get("NFFTB200_NO_PLAN_REUSE") is None
 
 
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
@@ -29,15 +37,44 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     if ws is None or ws.numel() < nbytes:
         ws = None
         _workspaces.pop(key, None)
+        _sorted_points.pop(key, None)
         ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
 
 def clear_caches():
-    """Drop cached workspaces and cuFFT plans."""
+    """Drop cached workspaces, remembered point sorts and cuFFT plans."""
     _workspaces.clear()
+    _sorted_points.clear()
     _lib.lib().nfftb200_plan_cache_clear()
+
+
+def forget_sorted_points():
+    """Forget which point sets the workspaces hold a sort for (the next transform bins again)."""
+    _sorted_points.clear()
+
+
+def _points_identity(pos, batch, geometry):
+    """Identity of a sorted point set: the tensor objects (weakly held) at their current version plus
+    the tiling the sort was made for.  In-place writes through torch bump `_version`."""
+    return (weakref.ref(pos), pos._version, None if batch is None else weakref.ref(batch),
+            None if batch is None else batch._version, geometry)
+
+
+def _same_points(ident, pos, batch, geometry):
+    if ident is None or not _PLAN_REUSE:
+        return False
+    rpos, vpos, rbatch, vbatch, geom = ident
+    if rpos() is not pos or vpos != pos._version or geom != geometry:
+        return False
+    if batch is None:
+        return rbatch is None
+    return rbatch is not None and rbatch() is batch and vbatch == batch._version
+
+
+def _ws_key(device):
+    return (device.index, torch.cuda.current_stream(device).cuda_stream)
 
 
 def _stream_ptr(device):
@@ -101,8 +138,14 @@ def _op_adjoint(pos, x, batch, N, m, real_output, batch_size=None):
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_ADJOINT, n, 0, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, pos.device)
+        geometry = tuple(_lib.geometry(d, N, m, B, C, flags & _lib.X_COMPLEX, n).values())
+        key = _ws_key(pos.device)
+        if _same_points(_sorted_points.get(key), pos, batch, geometry):
+            flags |= _lib.PRESORTED
+        _sorted_points.pop(key, None)
         _lib.check(L.nfftb200_adjoint(_ptr(pos), _ptr(x), _ptr(batch), _ptr(y), n, d, N, m, B, C, flags,
                                       ws.data_ptr(), ws.numel(), _stream_ptr(pos.device)), "nfft_adjoint")
+        _sorted_points[key] = _points_identity(pos, batch, geometry)
     return y
 
 
@@ -130,8 +173,15 @@ def _op_forward(pos, xhat, batch, m, real_output, batch_size=None):
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_FORWARD, 0, n, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, pos.device)
+        # the gather grid is complex unless real_output: same tiling rule as a complex adjoint
+        geometry = tuple(_lib.geometry(d, N, m, B, C, 0 if real_output else _lib.X_COMPLEX, n).values())
+        key = _ws_key(pos.device)
+        if _same_points(_sorted_points.get(key), pos, batch, geometry):
+            flags |= _lib.PRESORTED
+        _sorted_points.pop(key, None)
         _lib.check(L.nfftb200_forward(_ptr(pos), _ptr(xhat), _ptr(batch), _ptr(y), n, d, N, m, B, C, flags,
                                       ws.data_ptr(), ws.numel(), _stream_ptr(pos.device)), "nfft_forward")
+        _sorted_points[key] = _points_identity(pos, batch, geometry)
     return y
 
 
@@ -167,6 +217,7 @@ def _op_fastsum(sources, targets, x, coeffs, source_batch, target_batch, m, batc
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_FASTSUM, n_src, n_tgt, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, x.device)
+        _sorted_points.pop(_ws_key(x.device), None)
         _lib.check(L.nfftb200_fastsum(_ptr(sources_c), _ptr(targets_c), _ptr(x), _ptr(coeffs), _ptr(source_batch),
                                       _ptr(target_batch), _ptr(y), n_src, n_tgt, d, N, m, B, C, flags,
                                       ws.data_ptr(), ws.numel(), _stream_ptr(x.device)), "nfft_fastsum")
