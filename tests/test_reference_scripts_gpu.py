@@ -1,0 +1,173 @@
+"""The reference's five print-only test scripts (reference test/*.py) re-expressed as asserting,
+seeded pytest cases with the reference's own parameters; thresholds are the NFFT's approximation
+error at those parameters with a small margin.  Plus the new capability the
+BASELINE asks for: gradients w.r.t. the point positions (oracle: autograd through ndft_*)."""
+import numpy as np
+import pytest
+import torch
+
+import torch_nfft_b200 as torch_nfft
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b, p=2):
+    return (torch.linalg.vector_norm((a - b).flatten(), ord=p) / torch.linalg.vector_norm(b.flatten(), ord=p)).item()
+
+
+def test_adjoint_script():
+    """reference test/test_adjoint.py:21-49 (points on a circle of radius 1/4, N=16, m=4, b=3, c=10),
+    called with the script's own N=/m= keywords."""
+    torch.manual_seed(0)
+    d, b, n, c, N, m = 2, 3, 1000, 10, 16, 4
+    pos = torch.rand((n * b, d)).cuda() - 0.5
+    pos /= 4 * torch.linalg.norm(pos, dim=1, keepdim=True)
+    batch = torch.div(torch.arange(n * b).cuda(), n, rounding_mode="trunc")
+    x = torch.rand((n * b, c)).cuda()
+    y_nfft = torch_nfft.nfft_adjoint(x, pos, batch, N=N, m=m)
+    assert y_nfft.shape == (b, N, N, c)
+    y_ndft = torch.cat([torch_nfft.ndft_adjoint(x[:, i], pos, batch, N=N)[..., None] for i in range(c)], dim=-1)
+    assert rel(y_nfft, y_ndft, 1) < 3e-4 and rel(y_nfft, y_ndft, 2) < 3e-4
+    assert rel(y_nfft, y_ndft, float("inf")) < 3e-4
+
+
+def test_forward_script():
+    """reference test/test_forward.py:21-51 (real x-hat, n=10, N=16, m=4)."""
+    torch.manual_seed(1)
+    d, b, n, c, N, m = 2, 1, 10, 1, 16, 4
+    pos = torch.rand((n * b, d)).cuda() - 0.5
+    x = torch.rand((b, N, N, c)).cuda()
+    y_nfft = torch_nfft.nfft_forward(x, pos, None, m=m)
+    y_ndft = torch_nfft.ndft_forward(x, pos, None)
+    assert y_nfft.shape == (n, c) and y_nfft.is_complex()
+    assert rel(y_nfft, y_ndft) < 3e-4
+
+
+@pytest.mark.parametrize("kind", ["analytic", "interpolated_p0"])
+def test_fastsum_script(kind):
+    """reference test/test_fastsum.py:9-68 (n=200, sigma=0.2, N=8, m=3, x = identity)."""
+    torch.manual_seed(2)
+    n, dim, sigma, N, m = 200, 2, 0.2, 8, 3
+    pos = torch.rand((n, dim)).cuda() - 0.5
+    pos /= 4 * torch.linalg.norm(pos, dim=1).max()
+    A_true = torch.exp(-(pos.reshape(1, n, dim) - pos.reshape(n, 1, dim)).pow(2).sum(-1) / sigma ** 2)
+    coeffs = (torch_nfft.gaussian_analytic_coeffs(sigma, dim=dim, N=N) if kind == "analytic"
+              else torch_nfft.gaussian_interpolated_coeffs(sigma, dim=dim, N=N, p=0))
+    A_nfft = torch_nfft.nfft_fastsum(torch.eye(n).cuda(), coeffs, pos, cutoff=m)
+    A_trig = torch_nfft.exact_trigonometric_matrix(coeffs, pos).real
+    assert (A_trig - A_true).abs().max().item() < 2e-3       # the kernel's own truncation error at N=8
+    assert (A_nfft - A_trig).abs().max().item() < 2e-3       # the NFFT error at m=3
+    assert (A_nfft - A_true).abs().max().item() < 4e-3
+
+
+def _fd_grad(fn, x, eps=1e-3):
+    loss = fn(x)
+    g = torch.zeros_like(x)
+    for i in np.ndindex(*x.shape):
+        x[i] += eps
+        g[i] = (fn(x) - loss) / eps
+        x[i] -= eps
+    return g
+
+
+def test_grad_script():
+    """reference test/test_grad.py:8-102: autograd w.r.t. x of adjoint / forward (real x-hat) / fastsum
+    against forward finite differences (step 1e-3)."""
+    torch.manual_seed(3)
+    n, dim, b, c, N, m = 5, 2, 2, 3, 16, 3
+    pos = torch.rand((n * b, dim)).cuda() - 0.5
+    pos /= 4 * torch.linalg.norm(pos, dim=1).max()
+    batch = torch.div(torch.arange(n * b).cuda(), n, rounding_mode="trunc")
+
+    x = torch.rand((n * b, c), device="cuda", requires_grad=True)
+    torch_nfft.nfft_adjoint(x, pos, batch, N, m).abs().sum().backward()
+    fd = _fd_grad(lambda v: torch_nfft.nfft_adjoint(v, pos, batch, N, m).abs().sum(), x.detach().clone())
+    assert (x.grad - fd).abs().max().item() / fd.abs().max().item() < 2e-2
+
+    xh = torch.rand((b, N, N, c), device="cuda", requires_grad=True)
+    torch_nfft.nfft_forward(xh, pos, batch, m).abs().sum().backward()
+    fd = _fd_grad(lambda v: torch_nfft.nfft_forward(v, pos, batch, m).abs().sum(), xh.detach().clone())
+    assert xh.grad.dtype == torch.float32  # real input -> real gradient (reference nfft.py:52)
+    assert (xh.grad - fd).abs().max().item() / fd.abs().max().item() < 2e-2
+
+    x = torch.rand((n * b, c), device="cuda", requires_grad=True)
+    coeffs = torch_nfft.gaussian_interpolated_coeffs(0.2, dim, N)
+    torch_nfft.nfft_fastsum(x, coeffs, pos, batch=batch, cutoff=m).abs().sum().backward()
+    fd = _fd_grad(lambda v: torch_nfft.nfft_fastsum(v, coeffs, pos, batch=batch, cutoff=m).abs().sum(), x.detach().clone())
+    assert (x.grad - fd).abs().max().item() / fd.abs().max().item() < 2e-2
+    with pytest.raises(AssertionError):  # reference nfft.py:66-69
+        torch_nfft.nfft_fastsum(x, coeffs, pos.clone().requires_grad_(), batch=batch, cutoff=m)
+
+
+def test_grad_matches_ndft_autograd_including_pos():
+    """Gradients w.r.t. x AND pos against autograd through the exact direct sums."""
+    torch.manual_seed(4)
+    n, dim, b, c, N, m = 40, 3, 2, 2, 16, 6
+    pos0 = (torch.rand((n * b, dim), device="cuda") - 0.5)
+    batch = torch.div(torch.arange(n * b).cuda(), n, rounding_mode="trunc")
+    w = torch.randn((b,) + (N,) * dim + (c,), device="cuda", dtype=torch.complex64)
+    for cplx in (False, True):
+        x0 = torch.randn((n * b, c), device="cuda", dtype=torch.complex64 if cplx else torch.float32)
+        grads = []
+        for fn in (torch_nfft.nfft_adjoint, torch_nfft.ndft_adjoint):
+            x, pos = x0.clone().requires_grad_(), pos0.clone().requires_grad_()
+            y = fn(x, pos, batch, N, m) if fn is torch_nfft.nfft_adjoint else fn(x, pos, batch, N=N)
+            (y * w.conj()).real.sum().backward()
+            grads.append((x.grad, pos.grad))
+        assert rel(grads[0][0], grads[1][0]) < 1e-4 and rel(grads[0][1], grads[1][1]) < 1e-4
+    v = torch.randn((n * b, c), device="cuda", dtype=torch.complex64)
+    for real_output in (False, True):
+        grads = []
+        for fn in (torch_nfft.nfft_forward, torch_nfft.ndft_forward):
+            xh, pos = w.clone().requires_grad_(), pos0.clone().requires_grad_()
+            y = fn(xh, pos, batch, m, real_output) if fn is torch_nfft.nfft_forward else fn(xh, pos, batch)
+            if real_output:
+                (y.real * v.real).sum().backward()
+            else:
+                (y * v.conj()).real.sum().backward()
+            grads.append((xh.grad, pos.grad))
+        assert rel(grads[0][0], grads[1][0]) < 1e-4 and rel(grads[0][1], grads[1][1]) < 1e-4
+
+
+def test_kernel_script():
+    """reference test/test_kernel.py:7-58: GaussianKernel(...)(pos, batch).to_dense() vs the exact
+    Gaussian matrix (the batched path needs torch_scatter in the reference; not here)."""
+    torch.manual_seed(5)
+    n, dim, b, diameter = 4, 2, 2, 10.0
+    pos = diameter * (torch.rand((n * b, dim), device="cuda") - 0.5)
+    batch = torch.div(torch.arange(n * b).cuda(), n, rounding_mode="trunc")
+
+    def check(kernel, sigma, tol):
+        A = kernel(pos, batch=batch)
+        dense = A.to_dense()
+        exact = torch_nfft.exact_gaussian_matrix(sigma, pos, batch=batch)
+        assert A.is_symmetric() and dense.shape == (n * b, n * b)
+        err = (dense - exact).abs().max().item() / exact.abs().max().item()
+        assert err < tol, err
+        assert torch.allclose(A.row_sums(), dense.sum(1), atol=1e-3)
+        return dense, exact
+
+    # the reference script's own parameters: sigma = diameter, N = 16, m = 3, p = 0 (absolute sigma)
+    check(torch_nfft.GaussianKernel(diameter, dim, 16, 3, shift_by_center=True, max_infinity_norm=diameter / 2,
+                                    reg_degree=0), diameter, 5e-2)
+    # a well-resolved kernel: the error is the NFFT's
+    sigma = 2.0
+    for kwargs in ({"max_infinity_norm": diameter / 2, "shift_by_center": False}, {"max_euclidean_norm": diameter, "analytic": True}):
+        kernel = torch_nfft.GaussianKernel(sigma, dim=dim, bandwidth=32, cutoff=4, **kwargs)
+        dense, exact = check(kernel, sigma, 1e-3)
+    # relative sigma: every point set is scaled by its own radius rho -> kernel exp(-|z|^2 / (rho sigma)^2)
+    kernel = torch_nfft.GaussianKernel(0.3, dim=dim, bandwidth=32, cutoff=4)
+    dense = kernel(pos, batch=batch).to_dense()
+    for k in range(b):
+        sel = batch == k
+        pk = pos[sel] - 0.5 * (pos[sel].min(0).values + pos[sel].max(0).values)
+        rho = pk.abs().max().item()
+        ek = torch_nfft.exact_gaussian_matrix(0.3 * rho, pos[sel])
+        assert (dense[sel][:, sel] - ek).abs().max().item() < 2e-3
+    # adjacency matrix on top (the reference raises NameError here, matrices.py:149)
+    kernel = torch_nfft.GaussianKernel(sigma, dim=dim, bandwidth=32, cutoff=4, max_infinity_norm=diameter / 2)
+    exact = torch_nfft.exact_gaussian_matrix(sigma, pos, batch=batch)
+    lap = kernel.adjacency_matrix(pos, batch=batch, normalization="sym", shift="laplacian").to_dense()
+    deg = exact.sum(1)
+    expect = torch.eye(n * b, device="cuda") - exact / deg.sqrt()[:, None] / deg.sqrt()[None, :]
+    assert (lap - expect).abs().max().item() < 2e-3
