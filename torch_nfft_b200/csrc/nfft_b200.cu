@@ -560,13 +560,13 @@ int nfftb200_version(void) { return 100; }
 const char* nfftb200_last_error(void) { return g_err; }
 int64_t nfftb200_launch_count(void) { return (int64_t)g_launches.load(); }
 
-// out[0..19] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads
+// out[0..20] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads, use_reg
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n, int32_t* out) {
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    int v[20] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
-                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.use_reg ? -g.spread_threads : g.spread_threads};
-    for (int i = 0; i < 20; ++i) out[i] = v[i];
+    int v[21] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
+                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg};
+    for (int i = 0; i < 21; ++i) out[i] = v[i];
     return NFFTB200_OK;
 }
 
