@@ -203,14 +203,16 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     float* win = s_win + warp * (kRegGroup * 3 * WP);
     const int padx = g.org[0] - g.m;
     const bool pow2 = (g.M & (g.M - 1)) == 0;
-    // (x, y) positions of the register block owned by this lane: c = lane + 32 q -> (c % WX, c / WX),
-    // packed as window indices  i | (WP + j) << 8  (invalid positions read the always-zero entry WP-1)
-    int ij[CPL];
+    // (x, y) positions of the register block owned by this lane: c = lane + 32 q -> (c % WX, c / WX);
+    // wi / wj index the x / y tap windows (invalid positions read the always-zero entry WP-1)
+    int wi[CPL], wj[CPL], coff[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
         const bool ok = c < Cfg::COLS;
-        ij[q] = ok ? (c % WX) | (WP + c / WX) << 8 : (WP - 1) | (2 * WP - 1) << 8;
+        wi[q] = ok ? c % WX : WP - 1;
+        wj[q] = ok ? WP + c / WX : 2 * WP - 1;
+        coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
 
     // columns of supercells are handed out dynamically, one per warp
@@ -230,44 +232,12 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = make_float2(0.f, 0.f);
 
-        for (int scz = 0; scz < nsz; ++scz) {
-            const int lo = s_start[c0 + scz], hi = s_start[c0 + scz + 1];
-            for (int base = lo; base < hi; base += kRegGroup) {
-                const int npts = hi - base < kRegGroup ? hi - base : kRegGroup;
-                stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
-                const float* wv = win;
-#if NFFT_REG_PTLOOP
-                for (int gp = 0; gp < npts; ++gp, wv += 3 * WP) {
-#else
-#pragma unroll
-                for (int gp = 0; gp < kRegGroup; ++gp, wv += 3 * WP) {
-                    if (gp >= npts) continue;
-#endif
-                    const float xval = s_pts[base + gp].w;
-                    float2 wz[ZP];
-#pragma unroll
-                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                        const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
-                        wz[2 * l4] = make_float2(w4.x, w4.y);
-                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                    }
-                    float v[CPL];
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[ij[q] >> 8]) * wv[ij[q] & 0xff];
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const float2 vv = make_float2(v[q], v[q]);
-#pragma unroll
-                        for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
-                    }
-                }
-                __syncwarp();
-            }
-            // planes 0 .. SZ-1 of the block are complete: add them out, slide the block up by SZ.
-            // Other warps' blocks overlap this one in x/y, so each pair of tile planes is guarded by
-            // a shared-memory lock; inside it the update is a plain pipelined LDS / FADD / STS
-            // (a shared-memory float atomicAdd is a CAS loop per element on sm_100a).
-            const bool last = scz == nsz - 1;
+        // Planes 0 .. SZ-1 of the block at supercell `scz` are complete once its points are done:
+        // add them out and slide the block up by SZ (all planes when `last`).  Other warps' blocks
+        // overlap this one in x/y, so each pair of tile planes is guarded by a shared-memory lock;
+        // inside it the update is a plain pipelined LDS / FADD / STS (a shared-memory float
+        // atomicAdd is a CAS loop per element on sm_100a).
+        auto advance = [&](int scz, bool last) {
             const int zlim = g.P[2] - scz * SZ;  // planes of the padded tile above the block origin
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) {
@@ -282,14 +252,14 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     float2 cur[CPL];
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
-                        const float* src = pbase + ((ij[q] >> 8) - WP) * g.sY + (ij[q] & 0xff);
+                        const float* src = pbase + coff[q];
                         const bool ok = lane + 32 * q < Cfg::COLS;
                         cur[q].x = ok ? src[0] : 0.f;
                         cur[q].y = ok && two ? src[g.sZ] : 0.f;
                     }
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
-                        float* dst = pbase + ((ij[q] >> 8) - WP) * g.sY + (ij[q] & 0xff);
+                        float* dst = pbase + coff[q];
                         if (lane + 32 * q < Cfg::COLS) {
                             dst[0] = cur[q].x + acc[q][kp].x;
                             if (two) dst[g.sZ] = cur[q].y + acc[q][kp].y;
@@ -305,7 +275,43 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
                 for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = kp + SP < ZP ? acc[q][kp + SP] : make_float2(0.f, 0.f);
             }
+        };
+
+        // the column's points are staged in rounds of kRegGroup regardless of supercell boundaries
+        const int lo_col = s_start[c0], hi_col = s_start[c0 + nsz];
+        int scz = 0, next_end = s_start[c0 + 1];
+        for (int base = lo_col; base < hi_col; base += kRegGroup) {
+            const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
+            stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            const float* wv = win;
+            for (int gp = 0; gp < npts; ++gp, wv += 3 * WP) {
+                while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
+                    advance(scz, false);
+                    ++scz;
+                    next_end = s_start[c0 + scz + 1];
+                }
+                const float xval = s_pts[base + gp].w;
+                float2 wz[ZP];
+#pragma unroll
+                for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                    const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                    wz[2 * l4] = make_float2(w4.x, w4.y);
+                    wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
+                }
+                float v[CPL];
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[wj[q]]) * wv[wi[q]];
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const float2 vv = make_float2(v[q], v[q]);
+#pragma unroll
+                    for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
+                }
+            }
+            __syncwarp();
         }
+        for (; scz < nsz - 1; ++scz) advance(scz, false);
+        advance(nsz - 1, true);
     }
     __syncthreads();
 
@@ -358,12 +364,13 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     float* win = s_win + warp * (kRegGroup * 3 * WP);
     const int padx = g.org[0] - g.m;
     const bool pow2 = (g.M & (g.M - 1)) == 0;
-    int ij[CPL], coff[CPL];
+    int wi[CPL], wj[CPL], coff[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
         const bool ok = c < Cfg::COLS;
-        ij[q] = ok ? (c % WX) | (WP + c / WX) << 8 : (WP - 1) | (2 * WP - 1) << 8;
+        wi[q] = ok ? c % WX : WP - 1;
+        wj[q] = ok ? WP + c / WX : 2 * WP - 1;
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
     // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
@@ -385,14 +392,11 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) {
-                // pre-slide position: after the first slide pair kp holds planes 2 kp, 2 kp + 1
-                const int k = 2 * (kp - SP);
-                blk[q][kp] = kp >= SP ? make_float2(cbase[k * g.sZ + coff[q]], cbase[(k + 1) * g.sZ + coff[q]])
-                                      : make_float2(0.f, 0.f);
+                const int za = 2 * kp < zmax ? 2 * kp : zmax, zb = 2 * kp + 1 < zmax ? 2 * kp + 1 : zmax;
+                blk[q][kp] = make_float2(cbase[za * g.sZ + coff[q]], cbase[zb * g.sZ + coff[q]]);
             }
-
-        for (int scz = 0; scz < nsz; ++scz) {
-            // slide down by SZ and load the SZ new top planes
+        // move the block to supercell `scz`: slide down by SZ and load the SZ new top planes
+        auto advance = [&](int scz) {
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
 #pragma unroll
@@ -406,50 +410,57 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                     }
                 }
             }
-            const int lo = s_start[c0 + scz], hi = s_start[c0 + scz + 1];
-            for (int base = lo; base < hi; base += kRegGroup) {
-                const int npts = hi - base < kRegGroup ? hi - base : kRegGroup;
-                stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
-                float part[kRegGroup];
+        };
+
+        const int lo_col = s_start[c0], hi_col = s_start[c0 + nsz];
+        int scz = 0, next_end = s_start[c0 + 1];
+        for (int base = lo_col; base < hi_col; base += kRegGroup) {
+            const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
+            stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            float part[kRegGroup];
 #pragma unroll
-                for (int gp = 0; gp < kRegGroup; ++gp) part[gp] = 0.f;
-                const float* wv = win;
+            for (int gp = 0; gp < kRegGroup; ++gp) part[gp] = 0.f;
+            const float* wv = win;
 #pragma unroll
-                for (int gp = 0; gp < kRegGroup; ++gp, wv += 3 * WP) {
-                    if (gp < npts) {
-                        float2 wz[ZP];
-#pragma unroll
-                        for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                            const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
-                            wz[2 * l4] = make_float2(w4.x, w4.y);
-                            wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                        }
-                        float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int q = 0; q < CPL; ++q) {
-                            const float w = wv[ij[q] >> 8] * wv[ij[q] & 0xff];  // psi(Y) * psi(X)
-                            float2 inner = make_float2(0.f, 0.f);
-#pragma unroll
-                            for (int kp = 0; kp < ZP; ++kp) inner = ffma2(wz[kp], blk[q][kp], inner);
-                            sum = ffma2(make_float2(w, w), inner, sum);
-                        }
-                        part[gp] = sum.x + sum.y;
+            for (int gp = 0; gp < kRegGroup; ++gp, wv += 3 * WP) {
+                if (gp < npts) {
+                    while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
+                        ++scz;
+                        advance(scz);
+                        next_end = s_start[c0 + scz + 1];
                     }
-                }
+                    float2 wz[ZP];
 #pragma unroll
-                for (int gp = 0; gp < kRegGroup; ++gp) {
+                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                        const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                        wz[2 * l4] = make_float2(w4.x, w4.y);
+                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
+                    }
+                    float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) part[gp] += __shfl_xor_sync(0xffffffffu, part[gp], o);
-                }
-                if (lane < npts) {
-                    float v = part[0];
+                    for (int q = 0; q < CPL; ++q) {
+                        const float w = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X)
+                        float2 inner = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int gp = 1; gp < kRegGroup; ++gp) v = lane == gp ? part[gp] : v;
-                    const uint32_t i = (uint32_t)__float_as_int(s_pts[base + lane].w);
-                    a.yout[(size_t)i * g.K + a.k0] = v;
+                        for (int kp = 0; kp < ZP; ++kp) inner = ffma2(wz[kp], blk[q][kp], inner);
+                        sum = ffma2(make_float2(w, w), inner, sum);
+                    }
+                    part[gp] = sum.x + sum.y;
                 }
-                __syncwarp();
             }
+#pragma unroll
+            for (int gp = 0; gp < kRegGroup; ++gp) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part[gp] += __shfl_xor_sync(0xffffffffu, part[gp], o);
+            }
+            if (lane < npts) {
+                float v = part[0];
+#pragma unroll
+                for (int gp = 1; gp < kRegGroup; ++gp) v = lane == gp ? part[gp] : v;
+                const uint32_t i = (uint32_t)__float_as_int(s_pts[base + lane].w);
+                a.yout[(size_t)i * g.K + a.k0] = v;
+            }
+            __syncwarp();
         }
     }
     (void)WZ;
