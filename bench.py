@@ -119,6 +119,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic(kernel_substr):
+    """dram read+write bytes per launch of the dominant kernel from the latest committed ncu --set full
+    capture (profiles/rNN_roofline.json, written by scripts/summarise_profiles.py); None if absent."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        files = sorted(f for f in os.listdir(pdir) if f.endswith("_roofline.json"))
+        with open(os.path.join(pdir, files[-1])) as f:
+            data = json.load(f)
+        for name, v in data["kernels"].items():
+            if kernel_substr in name:
+                return v["dram_bytes_per_launch"], "profiles/" + files[-1]
+    except Exception:
+        pass
+    return None, None
+
+
 def cpu_baseline_ndft(workload, sample_points=192):
     """The reference's only host path: exact NDFT direct sums (reference torch_nfft/ndft.py:5-44),
     timed on this box's host cores on a bounded sample of the workload's point set."""
@@ -236,6 +252,7 @@ def run_ours(args):
         achieved = alg["spread"] / (spread_ms * 1e-3) / 1e9
         stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
         taps = n * C * (2 * m + 2) ** d
+        traffic, traffic_src = profiled_traffic("spread")
         out = {
             "metric": "NU points/sec (adjoint+forward)",
             "value": n * world / (ms_step * 1e-3),
@@ -258,9 +275,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * C * N ** d * 8 + n * C * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "spread_kernel (adjoint window convolution)",
+            "roofline": {"bound": "hbm", "kernel": "spread kernel (adjoint window convolution; spread_reg_kernel at c4)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg["spread"], "ms_per_launch": spread_ms,
                          "whole_step": {"algorithmic_bytes": alg["adjoint"] + alg["forward"],
                                         "achieved": (alg["adjoint"] + alg["forward"]) / (ms_step * 1e-3) / 1e9,
