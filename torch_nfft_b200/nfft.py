@@ -370,7 +370,7 @@ def nfft_forward(x, pos, batch=None, cutoff=3, real_output=False, *, m=None, bat
 
 
 def nfft_fastsum(x, coeffs, sources, targets=None, source_batch=None, target_batch=None, /, batch=None,
-                 cutoff=3, *, m=None, batch_size=None):
+                 cutoff=3, *, m=None, batch_size=None, differentiable_points=False):
     """Fast multiplication with the trigonometric kernel matrix
     A[t, s] = sum_l coeffs[l + N/2] exp(2 pi i l . (sources[s] - targets[t])).
 
@@ -380,7 +380,25 @@ def nfft_fastsum(x, coeffs, sources, targets=None, source_batch=None, target_bat
         nfft_fastsum(x, coeffs, sources, batch=batch)
         nfft_fastsum(x, coeffs, sources, targets, batch=batch)
         nfft_fastsum(x, coeffs, sources, targets, source_batch, target_batch)
-    Real x gives the real part (reference core_cuda.cu:814-818)."""
+    Real x gives the real part (reference core_cuda.cu:814-818).
+
+    `differentiable_points=True` (new; the reference asserts, nfft.py:66-69) evaluates the same
+    product as forward(coeffs * adjoint(x, sources), targets), which autograd can differentiate
+    w.r.t. x, coeffs, sources and targets."""
+    if differentiable_points:
+        if m is not None:
+            cutoff = m
+        if targets is None:
+            targets, target_batch = sources, source_batch
+        if batch is not None:
+            source_batch = target_batch = batch
+        N = coeffs.shape[0]
+        d = sources.shape[1]
+        spec = nfft_adjoint(x, sources, source_batch, N, int(cutoff), batch_size=batch_size)
+        cshape = (1,) + tuple(coeffs.shape) + (1,) * (spec.dim() - 1 - d)
+        out = nfft_forward(spec * coeffs.reshape(cshape), targets, target_batch, int(cutoff),
+                           real_output=not x.is_complex(), batch_size=spec.shape[0])
+        return out
     if targets is None:
         targets = sources
         target_batch = source_batch
