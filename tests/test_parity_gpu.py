@@ -382,3 +382,19 @@ def test_sort_reuse_between_adjoint_and_forward():
     f3 = T.nfft_forward(y, tp2, tb, 4, real_output=True)
     assert O.rel_l2(f3.cpu().numpy(), f.cpu().numpy()) < 1e-6
     assert nfft_mod._PLAN_REUSE
+
+
+def test_sort_reuse_is_invalidated_by_other_users_of_the_workspace():
+    """Split-stage calls (dist engine) and fastsum share the workspace: a remembered sort must not
+    survive them."""
+    from torch_nfft_b200 import dist as D
+    rng = np.random.default_rng(12)
+    pos, batch = make_points(rng, 3, 2, 4000)
+    x = make_values(rng, (pos.shape[0], 1), False)
+    tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
+    y = T.nfft_adjoint(tx, tp, tb, 32, 4)                      # remembers the sort of tp
+    half = pos.shape[0] // 2
+    D.CudaEngine().spread(tx[:half], tp[:half], tb[:half], 2, 32, 4)  # overwrites the sort region
+    f = T.nfft_forward(y, tp, tb, 4, real_output=True)          # must sort again
+    ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
+    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, 4, real_output=True)) < TOL

@@ -88,8 +88,12 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
             const int cy = wrap_mod((int)floorf(p1 * Mf), g.M) - lo1;
             const int cx = wrap_mod((int)floorf(p2 * Mf), g.M) - lo0;
             const int bx = cx / SX, by = cy / SY, bz = cz / SZ;
-            sc[k] = ((by * nsx + bx) * nsz + bz) | ((cx - bx * SX) | (cy - by * SY) << 2 | (cz - bz * SZ) << 4) << 24;
-            atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
+            // a point outside its tile can only come from a stale / foreign sort: drop it rather
+            // than index shared memory out of bounds
+            if (cx >= 0 && cy >= 0 && cz >= 0 && bx < nsx && by < nsy && bz < nsz) {
+                sc[k] = ((by * nsx + bx) * nsz + bz) | ((cx - bx * SX) | (cy - by * SY) << 2 | (cz - bz * SZ) << 4) << 24;
+                atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
+            }
         }
     }
     __syncthreads();

@@ -30,9 +30,12 @@ _sorted_points = {}
 _PLAN_REUSE = os.environ.get("NFFTB200_NO_PLAN_REUSE") is None
 
 
-def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Grow-only scratch tensor per (device, stream); allocated by the torch caching allocator."""
+def _workspace(nbytes: int, device: torch.device, keep_sorted: bool = False) -> torch.Tensor:
+    """Grow-only scratch tensor per (device, stream); allocated by the torch caching allocator.
+    Unless `keep_sorted`, the caller is about to overwrite the sort region: forget what it held."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    if not keep_sorted:
+        _sorted_points.pop(key, None)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = None
@@ -137,7 +140,7 @@ def _op_adjoint(pos, x, batch, N, m, real_output, batch_size=None):
     with torch.cuda.device(pos.device):
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_ADJOINT, n, 0, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
-        ws = _workspace(nbytes, pos.device)
+        ws = _workspace(nbytes, pos.device, keep_sorted=True)
         geometry = tuple(_lib.geometry(d, N, m, B, C, flags & _lib.X_COMPLEX, n).values())
         key = _ws_key(pos.device)
         if _same_points(_sorted_points.get(key), pos, batch, geometry):
@@ -172,7 +175,7 @@ def _op_forward(pos, xhat, batch, m, real_output, batch_size=None):
     with torch.cuda.device(pos.device):
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_FORWARD, 0, n, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
-        ws = _workspace(nbytes, pos.device)
+        ws = _workspace(nbytes, pos.device, keep_sorted=True)
         # the gather grid is complex unless real_output: same tiling rule as a complex adjoint
         geometry = tuple(_lib.geometry(d, N, m, B, C, 0 if real_output else _lib.X_COMPLEX, n).values())
         key = _ws_key(pos.device)
@@ -217,7 +220,6 @@ def _op_fastsum(sources, targets, x, coeffs, source_batch, target_batch, m, batc
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_FASTSUM, n_src, n_tgt, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, x.device)
-        _sorted_points.pop(_ws_key(x.device), None)
         _lib.check(L.nfftb200_fastsum(_ptr(sources_c), _ptr(targets_c), _ptr(x), _ptr(coeffs), _ptr(source_batch),
                                       _ptr(target_batch), _ptr(y), n_src, n_tgt, d, N, m, B, C, flags,
                                       ws.data_ptr(), ws.numel(), _stream_ptr(x.device)), "nfft_fastsum")
