@@ -42,6 +42,13 @@ struct RegCfg {
     static constexpr int ZQ = (WZ + 3) / 4;            // float4 loads per z window
     static constexpr int ZP = ZQ * 2;                  // float2 (packed fp32x2) accumulators per position
     static_assert(SZ % 2 == 0, "the block slides by whole float2 pairs");
+    // tap windows of one staging round in shared memory (per warp):
+    //   x / y windows: 2 * kRegGroup rows of XYP floats (odd pitch: conflict-free lane-per-window stores,
+    //                  entry XYP-1 is always zero), read as scalars
+    //   z windows    : kRegGroup rows of ZWP floats (16-byte aligned rows, read as float4)
+    static constexpr int XYP = (WX > WY ? WX : WY) + 1 + (((WX > WY ? WX : WY) + 1) % 2 == 0 ? 1 : 0);
+    static constexpr int ZWP = ZQ * 4 + 8;  // 20 floats: rows 16-byte aligned, row starts spread over the banks
+    static constexpr int WIN_FLOATS = (2 * kRegGroup * XYP + 3) / 4 * 4 + kRegGroup * ZWP;
 };
 
 // packed fp32x2 FMA (sm_100 FFMA2): d = a * b + c on both halves
@@ -55,7 +62,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 inline size_t reg_smem_bytes(const Geom& g, int nsc) {
     // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
-    return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * kRegGroup * 3 * 16 * 4 +
+    return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * RegCfg<10, 4, 4, 2>::WIN_FLOATS * 4 +
            (size_t)(2 * nsc + 4) * 4 + (size_t)kRegMaxPts + 64;
 }
 
@@ -128,45 +135,44 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
     __syncthreads();
 }
 
-// Phase A of a warp round: lanes 0 .. 3*LC-1 evaluate one window tap each for up to kRegGroup points
-// and store it at its shifted position inside the point's zero-initialised windows
-// (window order in shared memory: X, Y, Z).
-template <int LC, int WP>
+// Phase A of a warp round: the taps of up to kRegGroup points are evaluated and stored at their
+// shifted positions inside zero-initialised windows.  Lane <-> (point, dimension): each lane runs
+// L independent expf chains (unrolled), so the latency of one tap hides behind the others.
+template <typename Cfg, int LC>
 __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
                                               int npts, float* win, int lane, bool pow2) {
-    constexpr int kQuads = kRegGroup * 3 * WP / 4;
+    constexpr int kQuads = Cfg::WIN_FLOATS / 4;
 #pragma unroll
     for (int k = 0; k < (kQuads + 31) / 32; ++k) {
         const int qd = lane + 32 * k;
         if (qd < kQuads) reinterpret_cast<float4*>(win)[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
-    if (lane < 3 * LC) {
-        const int api = lane / LC, l = lane - api * LC;  // API dim 0,1,2 <-> slot Z,Y,X
+    const int pt = lane / 3, api = lane - pt * 3;  // API dim 0,1,2 <-> slot Z,Y,X
+    if (pt < npts) {
         const int slot = 2 - api;
-        const float Mf = (float)g.M;
-        const float ml = (float)(g.m - l);
-        const float* pcoord = reinterpret_cast<const float*>(s_pts + base) + api;
-        float* wdst = win + slot * WP + l;
-        // kRegGroup independent dependency chains (unrolled): the expf latency of one point hides
-        // behind the others.  Slots beyond npts compute on stale data and are not stored.
+        const float p = reinterpret_cast<const float*>(s_pts + base + pt)[api];
+        const int off = (s_off[base + pt] >> (2 * slot)) & 3;
+        constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;
+        float* dst = slot == 2 ? win + kXY + pt * Cfg::ZWP + off : win + (2 * pt + slot) * Cfg::XYP + off;
+        const float pm = p * (float)g.M;
+        const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
+        if (pow2) {
+            // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
+            // rounded, i.e. identical to the reference's double evaluation (:84-86)
+            const float fr = (pm - fl) + (float)g.m;
 #pragma unroll
-        for (int gp = 0; gp < kRegGroup; ++gp) {
-            const int off = (s_off[base + gp] >> (2 * slot)) & 3;
-            const float p = pcoord[4 * gp];
-            const float pm = p * Mf;
-            const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
-            float tt;
-            if (pow2) {
-                // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or
-                // correctly rounded, i.e. identical to the reference's double evaluation
-                tt = (pm - fl) + ml;
-            } else {
-                const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
-                tt = (float)(bd - (double)l);
+            for (int l = 0; l < LC; ++l) {
+                const float tt = fr - (float)l;
+                dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
-            const float val = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
-            if (gp < npts) wdst[gp * 3 * WP + off] = val;
+        } else {
+            const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                const float tt = (float)(bd - (double)l);
+                dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;
+            }
         }
     }
     __syncwarp();
@@ -179,7 +185,7 @@ template <int LC, int SX, int SY, int SZ>
 __global__ void __launch_bounds__(kRegThreads, 2)
 spread_reg_kernel(const Geom g, const WindowArgs a) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
-    constexpr int WX = Cfg::WX, WP = Cfg::WP, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
+    constexpr int WX = Cfg::WX, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
@@ -189,7 +195,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     float* tile = smem;
     float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
     float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
-    int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * kRegGroup * 3 * WP);
+    int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
     int* s_cur = s_start + nsc + 2;
     unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
     __shared__ int s_next;
@@ -204,7 +210,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* win = s_win + warp * (kRegGroup * 3 * WP);
+    float* win = s_win + warp * Cfg::WIN_FLOATS;
+    constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;  // z windows start here
     const int padx = g.org[0] - g.m;
     const bool pow2 = (g.M & (g.M - 1)) == 0;
     // (x, y) positions of the register block owned by this lane: c = lane + 32 q -> (c % WX, c / WX);
@@ -214,8 +221,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
         const bool ok = c < Cfg::COLS;
-        wi[q] = ok ? c % WX : WP - 1;
-        wj[q] = ok ? WP + c / WX : 2 * WP - 1;
+        wi[q] = ok ? c % WX : Cfg::XYP - 1;               // x window row (slot 0) of the point
+        wj[q] = ok ? Cfg::XYP + c / WX : 2 * Cfg::XYP - 1;  // y window row (slot 1)
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
 
@@ -286,9 +293,10 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         int scz = 0, next_end = s_start[c0 + 1];
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
-            stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
-            const float* wv = win;
-            for (int gp = 0; gp < npts; ++gp, wv += 3 * WP) {
+            stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            const float* wv = win;          // x / y windows of the point
+            const float* wzp = win + kXY;   // z window of the point
+            for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
                 while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
                     advance(scz, false);
                     ++scz;
@@ -298,7 +306,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                 float2 wz[ZP];
 #pragma unroll
                 for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                    const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                    const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
                     wz[2 * l4] = make_float2(w4.x, w4.y);
                     wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
                 }
@@ -337,7 +345,7 @@ template <int LC, int SX, int SY, int SZ>
 __global__ void __launch_bounds__(kRegThreads, 2)
 gather_reg_kernel(const Geom g, const WindowArgs a) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
-    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, WP = Cfg::WP, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
+    constexpr int WX = Cfg::WX, WZ = Cfg::WZ, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
@@ -347,7 +355,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     float* tile = smem;
     float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
     float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
-    int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * kRegGroup * 3 * WP);
+    int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
     int* s_cur = s_start + nsc + 2;
     unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
     __shared__ int s_next;
@@ -365,7 +373,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* win = s_win + warp * (kRegGroup * 3 * WP);
+    float* win = s_win + warp * Cfg::WIN_FLOATS;
+    constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;  // z windows start here
     const int padx = g.org[0] - g.m;
     const bool pow2 = (g.M & (g.M - 1)) == 0;
     int wi[CPL], wj[CPL], coff[CPL];
@@ -373,8 +382,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
         const bool ok = c < Cfg::COLS;
-        wi[q] = ok ? c % WX : WP - 1;
-        wj[q] = ok ? WP + c / WX : 2 * WP - 1;
+        wi[q] = ok ? c % WX : Cfg::XYP - 1;               // x window row (slot 0) of the point
+        wj[q] = ok ? Cfg::XYP + c / WX : 2 * Cfg::XYP - 1;  // y window row (slot 1)
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
     // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
@@ -420,13 +429,14 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         int scz = 0, next_end = s_start[c0 + 1];
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
-            stage_windows<LC, WP>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
             float part[kRegGroup];
 #pragma unroll
             for (int gp = 0; gp < kRegGroup; ++gp) part[gp] = 0.f;
             const float* wv = win;
+            const float* wzp = win + kXY;
 #pragma unroll
-            for (int gp = 0; gp < kRegGroup; ++gp, wv += 3 * WP) {
+            for (int gp = 0; gp < kRegGroup; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
                 if (gp < npts) {
                     while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
                         ++scz;
@@ -436,7 +446,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                     float2 wz[ZP];
 #pragma unroll
                     for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                        const float4 w4 = reinterpret_cast<const float4*>(wv + 2 * WP)[l4];
+                        const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
                         wz[2 * l4] = make_float2(w4.x, w4.y);
                         wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
                     }
