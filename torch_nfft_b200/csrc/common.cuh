@@ -92,7 +92,7 @@ struct SortPlan {
     uint32_t* perm;         // [n]  stable permutation (sorted position -> input index)
     uint32_t* bin_start;    // [nbins+1]
     uint32_t* chunk_start;  // [nbins+1]; chunk_start[nbins] = number of work items
-    int2* items;            // [max_items] (bin, chunk)
+    uint4* items;           // [max_items] {bin, first point, one past last point, 0}; zero beyond the last item
     long long nbins;
     long long max_items;
 };

@@ -261,12 +261,22 @@ chunk_count_kernel(const uint32_t* __restrict__ bin_start, long long nbins, int 
     nch[b] = (c + (uint32_t)pmax - 1u) / (uint32_t)pmax;
 }
 
+// items[w] = {bin, first point, one past the last point, 0}: the points of a bin are split evenly
+// over its chunks.  Entries beyond the last work item stay zero (empty range), so a CTA needs one
+// 16-byte load to know its work.
 __global__ void __launch_bounds__(256)
-fill_items_kernel(const uint32_t* __restrict__ chunk_start, long long nbins, int2* __restrict__ items) {
+fill_items_kernel(const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ chunk_start, long long nbins,
+                  uint4* __restrict__ items) {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbins) return;
     const uint32_t lo = chunk_start[b], hi = chunk_start[b + 1];
-    for (uint32_t w = lo; w < hi; ++w) items[w] = make_int2((int)b, (int)(w - lo));
+    const uint32_t p0 = bin_start[b];
+    const unsigned long long cnt = bin_start[b + 1] - p0;
+    const uint32_t nch = hi - lo;
+    for (uint32_t w = lo; w < hi; ++w) {
+        const uint32_t c = w - lo;
+        items[w] = make_uint4((uint32_t)b, p0 + (uint32_t)(cnt * c / nch), p0 + (uint32_t)(cnt * (c + 1) / nch), 0u);
+    }
 }
 
 // ------------------------------------------------------------------------- host orchestration
@@ -297,7 +307,7 @@ inline SortLayout sort_layout(long long n, const Geom& g) {
     L.bin_start = take((size_t)(L.nbins + 1) * 4);
     L.nch = take((size_t)(L.nbins + 1) * 4);
     L.chunk_start = take((size_t)(L.nbins + 1) * 4);
-    L.items = take((size_t)L.max_items * sizeof(int2));
+    L.items = take((size_t)L.max_items * sizeof(uint4));
     L.table = take((size_t)(kRsBins * L.nblocks + 1) * 4);
     size_t s1 = scan_scratch_bytes(L.nbins + 1);
     size_t s2 = scan_scratch_bytes(kRsBins * L.nblocks + 1);
@@ -318,7 +328,7 @@ inline void sort_plan_pointers(long long n, const Geom& g, char* ws, SortPlan* p
     plan->perm = passes == 0 ? ibuf[0] : ibuf[(passes - 1) & 1];
     plan->bin_start = (uint32_t*)(ws + L.bin_start);
     plan->chunk_start = (uint32_t*)(ws + L.chunk_start);
-    plan->items = (int2*)(ws + L.items);
+    plan->items = (uint4*)(ws + L.items);
     plan->nbins = L.nbins;
     plan->max_items = L.max_items;
 }
@@ -371,7 +381,9 @@ inline int sort_points(const float* pos, const int64_t* batch, long long n, cons
     NF_TRY(scan_exclusive(bin_count, bin_start, L.nbins, scan, st));
     NF_LAUNCH(chunk_count_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, bin_start, L.nbins, g.pmax, nch);
     NF_TRY(scan_exclusive(nch, chunk_start, L.nbins, scan, st));
-    NF_LAUNCH(fill_items_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, chunk_start, L.nbins, plan->items);
+    NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)L.max_items * sizeof(uint4), st));
+    NF_LAUNCH(fill_items_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, bin_start, chunk_start, L.nbins,
+              plan->items);
     return NFFTB200_OK;
 }
 

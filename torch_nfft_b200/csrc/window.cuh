@@ -32,7 +32,7 @@ struct WindowArgs {
     const uint32_t* perm;
     const uint32_t* bin_start;
     const uint32_t* chunk_start;
-    const int2* items;
+    const uint4* items;
     long long nbins;
     int k0;                  // first component handled by this pass
 };
@@ -125,15 +125,11 @@ struct TileCtx {
 };
 
 __device__ __forceinline__ bool decode_item(const Geom& g, const WindowArgs& a, TileCtx& t) {
-    const uint32_t total = a.chunk_start[a.nbins];
-    if (blockIdx.x >= total) return false;
-    const int2 it = a.items[blockIdx.x];
-    const int bin = it.x;
-    const uint32_t lo = a.bin_start[bin], hi = a.bin_start[bin + 1];
-    const uint32_t nch = a.chunk_start[bin + 1] - a.chunk_start[bin];
-    const unsigned long long cnt = hi - lo;
-    t.p_lo = lo + (long long)(cnt * (unsigned long long)it.y / nch);
-    t.p_hi = lo + (long long)(cnt * (unsigned long long)(it.y + 1) / nch);
+    const uint4 it = __ldg(a.items + blockIdx.x);
+    if (it.y == it.z) return false;  // beyond the last work item
+    const int bin = (int)it.x;
+    t.p_lo = it.y;
+    t.p_hi = it.z;
     t.b = bin / g.tiles_per_batch;
     int r = bin - t.b * g.tiles_per_batch;
     const int tx = r % g.nt[0];

@@ -20,7 +20,10 @@ namespace nfftb200 {
 
 constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
-constexpr int kRegMaxPts = 1536;  // points per work item (chunk) held in shared memory
+#ifndef NFFT_REG_MAXPTS
+#define NFFT_REG_MAXPTS 1536
+#endif
+constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) held in shared memory
 #ifndef NFFT_REG_GROUP
 #define NFFT_REG_GROUP 8
 #endif
@@ -135,6 +138,21 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
     __syncthreads();
 }
 
+// Columns are processed longest first (LPT): with dynamic hand-out the last warp to finish then
+// holds a short column.  s_order[rank] = column; ncols <= 64.
+__device__ __forceinline__ void order_columns(const int* s_start, int ncols, int nsz, int* s_order) {
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        const int cnt = s_start[(c + 1) * nsz] - s_start[c * nsz];
+        int rank = 0;
+        for (int o = 0; o < ncols; ++o) {
+            const int oc = s_start[(o + 1) * nsz] - s_start[o * nsz];
+            rank += (oc > cnt || (oc == cnt && o < c)) ? 1 : 0;
+        }
+        s_order[rank] = c;
+    }
+    __syncthreads();
+}
+
 // Phase A of a warp round: the taps of up to kRegGroup points are evaluated and stored at their
 // shifted positions inside zero-initialised windows.  Lane <-> (point, dimension): each lane runs
 // L independent expf chains (unrolled), so the latency of one tap hides behind the others.
@@ -208,6 +226,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     __syncthreads();
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    __shared__ int s_order[64];
+    order_columns(s_start, nsx * nsy, nsz, s_order);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = s_win + warp * Cfg::WIN_FLOATS;
@@ -232,8 +252,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         if (lane == 0) col = atomicAdd(&s_next, 1);
         col = __shfl_sync(0xffffffffu, col, 0);
         if (col >= nsx * nsy) break;
+        col = s_order[col];
         const int c0 = col * nsz;
-        if (s_start[c0] == s_start[c0 + nsz]) continue;  // empty column
+        if (s_start[c0] == s_start[c0 + nsz]) break;  // columns are ordered by size: the rest is empty
         const int scx = col % nsx, scy = col / nsx;
         float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
 
@@ -371,6 +392,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     __syncthreads();
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    __shared__ int s_order[64];
+    order_columns(s_start, nsx * nsy, nsz, s_order);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = s_win + warp * Cfg::WIN_FLOATS;
@@ -394,8 +417,9 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         if (lane == 0) col = atomicAdd(&s_next, 1);
         col = __shfl_sync(0xffffffffu, col, 0);
         if (col >= nsx * nsy) break;
+        col = s_order[col];
         const int c0 = col * nsz;
-        if (s_start[c0] == s_start[c0 + nsz]) continue;
+        if (s_start[c0] == s_start[c0 + nsz]) break;
         const int scx = col % nsx, scy = col / nsx;
         const float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
 
