@@ -30,10 +30,11 @@ constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) hel
 #ifndef NFFT_REG_FFMA2
 #define NFFT_REG_FFMA2 1
 #endif
-#ifndef NFFT_REG_PTLOOP
-#define NFFT_REG_PTLOOP 1
-#endif
 constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round
+#ifndef NFFT_REG_PTUNROLL
+#define NFFT_REG_PTUNROLL 1
+#endif
+constexpr int kPtUnroll = NFFT_REG_PTUNROLL;  // unroll factor of the spread point loop
 
 template <int LC, int SX, int SY, int SZ>
 struct RegCfg {
@@ -317,6 +318,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
             stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
             const float* wv = win;          // x / y windows of the point
             const float* wzp = win + kXY;   // z window of the point
+#pragma unroll kPtUnroll
             for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
                 while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
                     advance(scz, false);
