@@ -390,47 +390,72 @@ static int do_gather(const Geom& g, const float* pos, const int64_t* batch, cons
     return launch_window(false, g, a, sp, st);
 }
 
-template <int DIM>
-static int launch_unpack(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st) {
+// spectral kernels use 32-bit index arithmetic whenever every element index fits 31 bits
+template <int DIM, typename I>
+static int launch_unpack_t(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st) {
     long long total = (long long)g.B * g.C;
     for (int a = 0; a < DIM; ++a) total *= g.N;
     const unsigned grid = blocks_for(total);
     if (half) {
-        if (real_out) NF_LAUNCH((unpack_kernel<DIM, true, true>), grid, 256, 0, st, spec, y, g);
-        else NF_LAUNCH((unpack_kernel<DIM, true, false>), grid, 256, 0, st, spec, y, g);
+        if (real_out) NF_LAUNCH((unpack_kernel<DIM, true, true, I>), grid, 256, 0, st, spec, y, g);
+        else NF_LAUNCH((unpack_kernel<DIM, true, false, I>), grid, 256, 0, st, spec, y, g);
     } else {
-        if (real_out) NF_LAUNCH((unpack_kernel<DIM, false, true>), grid, 256, 0, st, spec, y, g);
-        else NF_LAUNCH((unpack_kernel<DIM, false, false>), grid, 256, 0, st, spec, y, g);
+        if (real_out) NF_LAUNCH((unpack_kernel<DIM, false, true, I>), grid, 256, 0, st, spec, y, g);
+        else NF_LAUNCH((unpack_kernel<DIM, false, false, I>), grid, 256, 0, st, spec, y, g);
     }
     return NFFTB200_OK;
 }
 
+template <int DIM, typename I>
+static int launch_pack_t(const Geom& g, bool half, bool xreal, const float* xhat, float2* spec, cudaStream_t st) {
+    // zero fill (out-of-band 7/8 of a 3D spectrum) with one memset, then write the band box
+    const long long total = half ? half_elems(g) : (long long)g.B * g.C * g.Md;
+    NF_CUDA(cudaMemsetAsync(spec, 0, (size_t)total * sizeof(float2), st));
+    long long band = (long long)g.B * g.C * (half ? g.N / 2 + 1 : g.N);
+    for (int a = 0; a < DIM - 1; ++a) band *= half ? g.N + 1 : g.N;
+    const unsigned grid = blocks_for(band);
+    if (half) {
+        if (xreal) NF_LAUNCH((pack_kernel<DIM, true, true, I>), grid, 256, 0, st, xhat, spec, g);
+        else NF_LAUNCH((pack_kernel<DIM, true, false, I>), grid, 256, 0, st, xhat, spec, g);
+    } else {
+        if (xreal) NF_LAUNCH((pack_kernel<DIM, false, true, I>), grid, 256, 0, st, xhat, spec, g);
+        else NF_LAUNCH((pack_kernel<DIM, false, false, I>), grid, 256, 0, st, xhat, spec, g);
+    }
+    return NFFTB200_OK;
+}
+
+template <int DIM, typename I>
+static int launch_multiply_t(const Geom& g, bool half, bool creal, float2* spec, const float* coeffs, cudaStream_t st) {
+    const long long total = half ? half_elems(g) : (long long)g.B * g.C * g.Md;
+    const unsigned grid = blocks_for(total);
+    if (half) {
+        if (creal) NF_LAUNCH((kernel_multiply_kernel<DIM, true, true, I>), grid, 256, 0, st, spec, coeffs, g);
+        else NF_LAUNCH((kernel_multiply_kernel<DIM, true, false, I>), grid, 256, 0, st, spec, coeffs, g);
+    } else {
+        if (creal) NF_LAUNCH((kernel_multiply_kernel<DIM, false, true, I>), grid, 256, 0, st, spec, coeffs, g);
+        else NF_LAUNCH((kernel_multiply_kernel<DIM, false, false, I>), grid, 256, 0, st, spec, coeffs, g);
+    }
+    return NFFTB200_OK;
+}
+
+static bool fits_int32(const Geom& g) {
+    // largest index any spectral kernel forms: complex grid elements plus one block of slack
+    return (long long)g.B * g.C * g.Md < (1ll << 31) - 1024;
+}
+template <int DIM>
+static int launch_unpack(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st) {
+    return fits_int32(g) ? launch_unpack_t<DIM, int>(g, half, real_out, spec, y, st)
+                         : launch_unpack_t<DIM, long long>(g, half, real_out, spec, y, st);
+}
 template <int DIM>
 static int launch_pack(const Geom& g, bool half, bool xreal, const float* xhat, float2* spec, cudaStream_t st) {
-    const long long total = half ? half_elems(g) : (long long)g.B * g.C * g.Md;
-    const unsigned grid = blocks_for(total);
-    if (half) {
-        if (xreal) NF_LAUNCH((pack_kernel<DIM, true, true>), grid, 256, 0, st, xhat, spec, g);
-        else NF_LAUNCH((pack_kernel<DIM, true, false>), grid, 256, 0, st, xhat, spec, g);
-    } else {
-        if (xreal) NF_LAUNCH((pack_kernel<DIM, false, true>), grid, 256, 0, st, xhat, spec, g);
-        else NF_LAUNCH((pack_kernel<DIM, false, false>), grid, 256, 0, st, xhat, spec, g);
-    }
-    return NFFTB200_OK;
+    return fits_int32(g) ? launch_pack_t<DIM, int>(g, half, xreal, xhat, spec, st)
+                         : launch_pack_t<DIM, long long>(g, half, xreal, xhat, spec, st);
 }
-
 template <int DIM>
 static int launch_multiply(const Geom& g, bool half, bool creal, float2* spec, const float* coeffs, cudaStream_t st) {
-    const long long total = half ? half_elems(g) : (long long)g.B * g.C * g.Md;
-    const unsigned grid = blocks_for(total);
-    if (half) {
-        if (creal) NF_LAUNCH((kernel_multiply_kernel<DIM, true, true>), grid, 256, 0, st, spec, coeffs, g);
-        else NF_LAUNCH((kernel_multiply_kernel<DIM, true, false>), grid, 256, 0, st, spec, coeffs, g);
-    } else {
-        if (creal) NF_LAUNCH((kernel_multiply_kernel<DIM, false, true>), grid, 256, 0, st, spec, coeffs, g);
-        else NF_LAUNCH((kernel_multiply_kernel<DIM, false, false>), grid, 256, 0, st, spec, coeffs, g);
-    }
-    return NFFTB200_OK;
+    return fits_int32(g) ? launch_multiply_t<DIM, int>(g, half, creal, spec, coeffs, st)
+                         : launch_multiply_t<DIM, long long>(g, half, creal, spec, coeffs, st);
 }
 
 #define NF_DIM_DISPATCH(fn, ...)                                   \

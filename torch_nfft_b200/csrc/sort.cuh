@@ -192,16 +192,25 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uin
 // In-order scatter.  Warp w of a block owns the contiguous items [base + w*512, +512) and walks
 // them 32 at a time, so (block, warp, round, lane) order == input order and equal digits keep
 // their relative order (stable).  idx_in == nullptr means the identity payload.
+// The block first sorts its 4096 items by digit in shared memory and then writes them out in that
+// order, so consecutive threads store to consecutive addresses of each digit's run (full sectors
+// instead of one 4-byte store per 32-byte sector).
 __global__ void __launch_bounds__(kRsThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, long long n, int shift,
                      const uint32_t* __restrict__ table_scanned, int nblocks) {
     __shared__ uint32_t wcnt[kRsWarps][kRsBins];
+    __shared__ uint32_t s_key[kRsTile];
+    __shared__ uint32_t s_idx[kRsTile];
+    __shared__ uint32_t s_loc[kRsBins];    // first position of a digit in the block-sorted order
+    __shared__ uint32_t s_gbase[kRsBins];  // first global position of this block's items of a digit
+    __shared__ uint32_t s_warp[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < kRsWarps * kRsBins; k += kRsThreads) (&wcnt[0][0])[k] = 0;
     __syncthreads();
 
-    const long long base = (long long)blockIdx.x * kRsTile + (long long)warp * (32 * kRsIpt);
+    const long long blk = (long long)blockIdx.x * kRsTile;
+    const long long base = blk + (long long)warp * (32 * kRsIpt);
     uint32_t key[kRsIpt];
     uint32_t rank[kRsIpt];
 #pragma unroll
@@ -222,27 +231,39 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         __syncwarp();
     }
     __syncthreads();
+    uint32_t total_d = 0;
     {
-        // exclusive prefix over the warps of this block, seeded with the global offset
+        // exclusive prefix over the warps of this block (block-local), per digit
         const int d = threadIdx.x;
-        uint32_t running = table_scanned[(long long)d * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < kRsWarps; ++w) {
-            uint32_t t = wcnt[w][d];
-            wcnt[w][d] = running;
-            running += t;
+            const uint32_t t = wcnt[w][d];
+            wcnt[w][d] = total_d;
+            total_d += t;
         }
+        s_gbase[d] = table_scanned[(long long)d * nblocks + blockIdx.x];
     }
+    uint32_t block_total;
+    const uint32_t loc = block_excl_scan(total_d, s_warp, &block_total);  // ends with __syncthreads
+    s_loc[threadIdx.x] = loc;
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < kRsIpt; ++s) {
         const long long i = base + s * 32 + lane;
         if (i < n) {
             const uint32_t digit = (key[s] >> shift) & 255u;
-            const uint32_t dst = wcnt[warp][digit] + rank[s];
-            keys_out[dst] = key[s];
-            idx_out[dst] = idx_in ? idx_in[i] : (uint32_t)i;
+            const uint32_t lp = s_loc[digit] + wcnt[warp][digit] + rank[s];
+            s_key[lp] = key[s];
+            s_idx[lp] = idx_in ? idx_in[i] : (uint32_t)i;
         }
+    }
+    __syncthreads();
+    for (uint32_t lp = threadIdx.x; lp < block_total; lp += kRsThreads) {
+        const uint32_t k = s_key[lp];
+        const uint32_t digit = (k >> shift) & 255u;
+        const uint32_t dst = s_gbase[digit] + (lp - s_loc[digit]);
+        keys_out[dst] = k;
+        idx_out[dst] = s_idx[lp];
     }
 }
 

@@ -27,23 +27,24 @@ __device__ __forceinline__ int wrapM(int k, int M) { return k < 0 ? k + M : k; }
 // adjoint unpack: spectrum (planar) -> y[b, i_0..i_{d-1}, c]
 //   HALF: spec is the R2C half spectrum [BC][M]..[M][M/2+1];  else full C2C (+ sign) [BC][M]^d
 // ---------------------------------------------------------------------------------------
-template <int DIM, bool HALF, bool REAL_OUT>
+// I = int when every index fits 31 bits (64-bit divisions are ~10x dearer), long long otherwise
+template <int DIM, bool HALF, bool REAL_OUT, typename I>
 __global__ void __launch_bounds__(256)
 unpack_kernel(const float2* __restrict__ spec, float* __restrict__ y, Geom g) {
-    const long long total = (long long)g.B * g.C;
-    long long nd = 1;
+    const I total = (I)g.B * g.C;
+    I nd = 1;
     for (int a = 0; a < DIM; ++a) nd *= g.N;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total * nd) return;
     const int c = (int)(idx % g.C);
-    long long f = idx / g.C;
+    I f = idx / g.C;
     int k[3] = {0, 0, 0};
 #pragma unroll
     for (int a = DIM - 1; a >= 0; --a) {
         k[a] = (int)(f % g.N) - g.N / 2;
         f /= g.N;
     }
-    const long long bc = f * g.C + c;
+    const I bc = f * g.C + c;
     float factor = 1.0f;
 #pragma unroll
     for (int a = 0; a < DIM; ++a) factor *= phi_hat_inv(k[a] < 0 ? -k[a] : k[a], g.c_hat);
@@ -52,14 +53,14 @@ unpack_kernel(const float2* __restrict__ spec, float* __restrict__ y, Geom g) {
     if (HALF) {
         const int H = g.M / 2 + 1;
         const bool neg = k[DIM - 1] < 0;
-        long long s = bc;
+        I s = bc;
 #pragma unroll
         for (int a = 0; a < DIM - 1; ++a) s = s * g.M + wrapM(neg ? -k[a] : k[a], g.M);
         s = s * H + (neg ? -k[DIM - 1] : k[DIM - 1]);
         v = spec[s];
         if (!neg) v.y = -v.y;
     } else {
-        long long s = bc;
+        I s = bc;
 #pragma unroll
         for (int a = 0; a < DIM; ++a) s = s * g.M + wrapM(k[a], g.M);
         v = spec[s];
@@ -75,14 +76,14 @@ unpack_kernel(const float2* __restrict__ spec, float* __restrict__ y, Geom g) {
 // forward pack: xhat[b, i.., c] -> spectrum (planar), deconvolved and zero padded
 // ---------------------------------------------------------------------------------------
 // decode a planar spectrum index into (bc, signed frequencies); returns false if idx out of range
-template <int DIM, bool HALF>
-__device__ __forceinline__ bool decode_spec(long long idx, const Geom& g, long long& bc, int kap[3]) {
+template <int DIM, bool HALF, typename I>
+__device__ __forceinline__ bool decode_spec(I idx, const Geom& g, I& bc, int kap[3]) {
     const int H = g.M / 2 + 1;
     const int last = HALF ? H : g.M;
-    long long per = last;
+    I per = last;
     for (int a = 0; a < DIM - 1; ++a) per *= g.M;
     if (idx >= per * g.B * g.C) return false;
-    long long r = idx;
+    I r = idx;
     int j = (int)(r % last);
     r /= last;
     kap[DIM - 1] = (HALF || j < g.M / 2) ? j : j - g.M;
@@ -110,9 +111,9 @@ __device__ __forceinline__ bool in_band(const int kap[3], int sign, int N) {
 }
 
 // index into channels-last [B][N]^d[C] for signed frequency sign*kap
-template <int DIM>
-__device__ __forceinline__ long long api_index(const int kap[3], int sign, long long b, int c, const Geom& g) {
-    long long s = b;
+template <int DIM, typename I>
+__device__ __forceinline__ I api_index(const int kap[3], int sign, I b, int c, const Geom& g) {
+    I s = b;
 #pragma unroll
     for (int a = 0; a < DIM; ++a) s = s * g.N + (sign * kap[a] + g.N / 2);
     return s * g.C + c;
@@ -127,15 +128,35 @@ __device__ __forceinline__ float rolloff(const int kap[3], float c_hat) {
 }
 
 // HALF = true : input of the C2R transform (Hermitian part, conjugated);  false: input of C2C(-).
-template <int DIM, bool HALF, bool XREAL>
+// The spectrum is zero outside the band, so the host zero-fills it with one memset and this kernel
+// visits only the band box: kappa_a in [-N/2, N/2] (HALF: last dim [0, N/2]) resp. [-N/2, N/2-1].
+template <int DIM, bool HALF, bool XREAL, typename I>
 __global__ void __launch_bounds__(256)
 pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long bc;
+    const int ext = HALF ? g.N + 1 : g.N;            // band extent of the leading dims
+    const int last = HALF ? g.N / 2 + 1 : g.N;       // band extent of the last dim
+    I per = last;
+    for (int a = 0; a < DIM - 1; ++a) per *= ext;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per * g.B * g.C) return;
     int kap[3] = {0, 0, 0};
-    if (!decode_spec<DIM, HALF>(idx, g, bc, kap)) return;
-    const long long b = bc / g.C;
+    I r = idx;
+    kap[DIM - 1] = (int)(r % last) - (HALF ? 0 : g.N / 2);
+    r /= last;
+#pragma unroll
+    for (int a = DIM - 2; a >= 0; --a) {
+        kap[a] = (int)(r % ext) - g.N / 2;
+        r /= ext;
+    }
+    const I bc = r;
+    const I b = bc / g.C;
     const int c = (int)(bc % g.C);
+    // position in the planar spectrum
+    I dst = bc;
+#pragma unroll
+    for (int a = 0; a < DIM - 1; ++a) dst = dst * g.M + wrapM(kap[a], g.M);
+    dst = dst * (HALF ? g.M / 2 + 1 : g.M) + (HALF ? kap[DIM - 1] : wrapM(kap[DIM - 1], g.M));
+
     const bool pos_in = in_band<DIM>(kap, 1, g.N);
     float2 out = make_float2(0.f, 0.f);
     if (HALF) {
@@ -144,7 +165,7 @@ pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
             const float factor = rolloff<DIM>(kap, g.c_hat);
             float re = 0.f, im = 0.f;
             if (pos_in) {  // conj(xhat[k])
-                const long long s = api_index<DIM>(kap, 1, b, c, g);
+                const I s = api_index<DIM, I>(kap, 1, b, c, g);
                 if (XREAL) {
                     re += xhat[s];
                 } else {
@@ -154,7 +175,7 @@ pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
                 }
             }
             if (neg_in) {  // xhat[-k]
-                const long long s = api_index<DIM>(kap, -1, b, c, g);
+                const I s = api_index<DIM, I>(kap, -1, b, c, g);
                 if (XREAL) {
                     re += xhat[s];
                 } else {
@@ -167,7 +188,7 @@ pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
         }
     } else if (pos_in) {
         const float factor = rolloff<DIM>(kap, g.c_hat);
-        const long long s = api_index<DIM>(kap, 1, b, c, g);
+        const I s = api_index<DIM, I>(kap, 1, b, c, g);
         if (XREAL) {
             out = make_float2(xhat[s] * factor, 0.f);
         } else {
@@ -175,7 +196,7 @@ pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
             out = make_float2(v.x * factor, v.y * factor);
         }
     }
-    spec[idx] = out;
+    spec[dst] = out;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -192,13 +213,13 @@ __device__ __forceinline__ long long coeff_index(const int kap[3], int sign, int
     return s;
 }
 
-template <int DIM, bool HALF, bool CREAL>
+template <int DIM, bool HALF, bool CREAL, typename I>
 __global__ void __launch_bounds__(256)
 kernel_multiply_kernel(float2* __restrict__ spec, const float* __restrict__ coeffs, Geom g) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long bc;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+    I bc;
     int kap[3] = {0, 0, 0};
-    if (!decode_spec<DIM, HALF>(idx, g, bc, kap)) return;
+    if (!decode_spec<DIM, HALF, I>(idx, g, bc, kap)) return;
     const bool pos_in = in_band<DIM>(kap, 1, g.N);
     const bool neg_in = HALF && in_band<DIM>(kap, -1, g.N);
     if (!pos_in && !neg_in) {
