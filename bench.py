@@ -78,7 +78,7 @@ class ClockSampler:
         self.rows, self.proc, self.thread = [], None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -195,14 +195,55 @@ def run_ours(args):
         y = T.nfft_adjoint(x, pos, batch, N, m, batch_size=B)
         return T.nfft_forward(y, pos, batch, m, real_output=True, batch_size=B)
 
+    # End-to-end arm: every step copies ITS inputs from pinned host memory and reads ITS results back.
+    # Like a data loader, the copies of step k+1 (copy stream) overlap the transforms of step k
+    # (compute stream) through two device buffer sets; results leave on a third stream.
+    compute_stream = torch.cuda.current_stream(dev)
+    h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dbuf = [(torch.empty_like(pos), torch.empty_like(x), torch.empty_like(batch)) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]   # inputs of the buffer set have arrived
+    ev_free = [torch.cuda.Event() for _ in range(2)]    # the transforms reading the buffer set are done
+    e2e_state = {"k": 0, "staged": False, "keep": None}
+
+    def stage_inputs(slot):
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(ev_free[slot])
+            dpos, dx, dbatch = dbuf[slot]
+            dpos.copy_(h_pos, non_blocking=True)
+            dx.copy_(h_x, non_blocking=True)
+            dbatch.copy_(h_batch, non_blocking=True)
+            ev_ready[slot].record(h2d_stream)
+
     def step_e2e():
-        dpos = h_pos.to(dev, non_blocking=True)
-        dx = h_x.to(dev, non_blocking=True)
-        dbatch = h_batch.to(dev, non_blocking=True)
+        k = e2e_state["k"]
+        slot = k % 2
+        if not e2e_state["staged"]:
+            stage_inputs(slot)                 # first step: nothing to overlap with
+        stage_inputs(1 - slot)                 # inputs of the NEXT step travel while this one computes
+        e2e_state["staged"] = True
+        compute_stream.wait_event(ev_ready[slot])
+        dpos, dx, dbatch = dbuf[slot]
         y = T.nfft_adjoint(dx, dpos, dbatch, N, m, batch_size=B)
         f = T.nfft_forward(y, dpos, dbatch, m, real_output=True, batch_size=B)
-        h_spec.copy_(y, non_blocking=True)
-        h_y.copy_(f, non_blocking=True)
+        ev_free[slot].record(compute_stream)
+        done = torch.cuda.Event()
+        done.record(compute_stream)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
+            h_spec.copy_(y, non_blocking=True)
+            h_y.copy_(f, non_blocking=True)
+        y.record_stream(d2h_stream)
+        f.record_stream(d2h_stream)
+        # the step is complete only when its results are on the host: the compute stream (which the
+        # timing events are recorded on) waits for this step's read-back before the next step ends
+        back = torch.cuda.Event()
+        back.record(d2h_stream)
+        e2e_state["keep"] = (y, f, back)
+        e2e_state["k"] = k + 1
+
+    def finish_e2e():
+        if e2e_state["keep"] is not None:
+            compute_stream.wait_event(e2e_state["keep"][2])
 
     def barrier():
         if world > 1:
@@ -224,6 +265,20 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
+    def timed_e2e(step, finish, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        finish()           # the compute stream waits for the last read-back
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), 0, 0
+
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -239,9 +294,16 @@ def run_ours(args):
     if args.no_extras:
         ms_e2e = float("nan")
     else:
+        for e in ev_free:
+            e.record(compute_stream)
         for _ in range(2):
             step_e2e()
-        ms_e2e, _, _ = timed(step_e2e, args.steps)
+        finish_e2e()
+        torch.cuda.synchronize()
+
+        # K timed steps; K+1 input sets are copied (the last prefetch is extra work inside the region)
+        e2e_state["k"] = 2
+        ms_e2e, _, _ = timed_e2e(step_e2e, finish_e2e, args.steps)
 
     if rank == 0:
         ms_step = ms_total / args.steps
