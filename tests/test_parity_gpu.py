@@ -53,6 +53,8 @@ CASES = [
     (2, 32, 4, 3, 700, 3),
     (2, 64, 3, 2, 1500, 8),
     (2, 16, 2, 1, 300, 10),
+    (2, 32, 4, 2, 900, 10),  # 2D register kernels: passes of 8 + 2 channels
+    (2, 32, 3, 1, 5000, 5),  # passes of 4 + 1, dense (5 points per cell)
     (3, 16, 3, 2, 600, 1),
     (3, 32, 4, 2, 2500, 1),
     (3, 16, 2, 1, 500, 3),

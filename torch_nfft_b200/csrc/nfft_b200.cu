@@ -10,6 +10,7 @@
 #include "spectral.cuh"
 #include "window.cuh"
 #include "window_reg.cuh"
+#include "window_reg2d.cuh"
 #include <stdlib.h>
 
 #include <initializer_list>
@@ -160,14 +161,19 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     const int maxc = d == 3 ? 2 : 8;
     while (ncomp * 2 <= g.K && ncomp * 2 <= maxc) ncomp *= 2;
     if (cplx && ncomp < 2) ncomp = 2;
-    // register-stencil kernels: 3D, m = 4, real grid, one component per pass
+    // register-stencil kernels: 3D, m <= 4, real grid, one component per pass
     static const bool no_reg = getenv("NFFTB200_NO_REG") != nullptr;
-    g.use_reg = (d == 3 && m == 4 && !cplx && !no_reg) ? 1 : 0;
+    g.use_reg = (d == 3 && m <= 4 && !cplx && !no_reg) ? 1 : 0;
     if (g.use_reg) ncomp = 1;
+    // 2D register-stencil kernels: m = 3 or 4, real grid, up to 8 channels per pass
+    if (d == 2 && (m == 3 || m == 4) && !cplx && !no_reg) g.use_reg = 2;
     g.ncomp = ncomp;
     int T[3] = {1, 1, 1};
     if (d == 1) {
         T[0] = 512;
+    } else if (d == 2 && g.use_reg == 2) {
+        T[0] = 32;
+        T[1] = 16;
     } else if (d == 2) {
         T[0] = ncomp >= 8 ? 32 : 64;
         T[1] = ncomp >= 4 ? 32 : 64;
@@ -199,7 +205,8 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
 
     long long pm = n_points / (148 * 8);
     g.pmax = (int)(pm < 256 ? 256 : (pm > 2048 ? 2048 : pm));
-    if (g.use_reg) g.pmax = kRegMaxPts;
+    if (g.use_reg == 1) g.pmax = kRegMaxPts;
+    if (g.use_reg == 2) g.pmax = kReg2MaxPts;
     int threads = (team + 31) / 32 * 32;
     g.spread_threads = threads < 64 ? 64 : threads;
     return NFFTB200_OK;
@@ -252,11 +259,52 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
     a.chunk_start = sp.chunk_start;
     a.items = sp.items;
     a.nbins = sp.nbins;
-    if (g.use_reg) {
-        // supercell 4 x 4 x 2 cells: register block 13 x 13 x 11, 5 rows of 13 accumulators per lane
-        WindowKernel kern = spread ? spread_reg_kernel<10, 4, 4, 2> : gather_reg_kernel<10, 4, 4, 2>;
+    if (g.use_reg == 2) {
+        // 2D: supercell 4 x 4 cells, up to 8 channels per pass (remaining channels in smaller passes)
+        int ncomp = g.ncomp;
+        for (int k0 = 0; k0 < g.K; k0 += ncomp) {
+            ncomp = g.ncomp;
+            while (ncomp > g.K - k0) ncomp >>= 1;
+            a.k0 = k0;
+            WindowKernel kern = nullptr;
+            int win_floats = 0;
+#define NF_REG2_CASE(L_, C_)                                                                              \
+            if (g.L == L_ && ncomp == C_) {                                                               \
+                kern = spread ? spread_reg2d_kernel<L_, C_> : gather_reg2d_kernel<L_, C_>;                \
+                win_floats = Reg2Cfg<L_, C_>::WIN_FLOATS;                                                 \
+            }
+            NF_REG2_CASE(8, 1) NF_REG2_CASE(8, 2) NF_REG2_CASE(8, 4) NF_REG2_CASE(8, 8)
+            NF_REG2_CASE(10, 1) NF_REG2_CASE(10, 2) NF_REG2_CASE(10, 4) NF_REG2_CASE(10, 8)
+#undef NF_REG2_CASE
+            if (!kern) NF_FAIL(NFFTB200_ERR_INVALID, "no 2D register-stencil kernel for L=%d ncomp=%d", g.L, ncomp);
+            const int nsc = ((g.T[0] + 3) / 4) * ((g.T[1] + 3) / 4);
+            const size_t smem = reg2_smem_bytes(g, ncomp, spread, nsc, win_floats);
+            if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
+            NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NF_LAUNCH(kern, (unsigned)sp.max_items, kReg2Threads, smem, st, g, a);
+        }
+        return NFFTB200_OK;
+    }
+    if (g.use_reg == 1) {
+        // supercell 4 x 4 x 2 cells; for m = 4 the register block is 13 x 13 x 12: 6 positions x 6
+        // float2 accumulators per lane
+        WindowKernel kern = nullptr;
+        int win_floats = 0;
+        switch (g.m) {
+#define NF_REG_CASE(M_, L_)                                                                          \
+            case M_:                                                                                 \
+                kern = spread ? spread_reg_kernel<L_, 4, 4, 2> : gather_reg_kernel<L_, 4, 4, 2>;     \
+                win_floats = RegCfg<L_, 4, 4, 2>::WIN_FLOATS;                                        \
+                break;
+            NF_REG_CASE(1, 4)
+            NF_REG_CASE(2, 6)
+            NF_REG_CASE(3, 8)
+            NF_REG_CASE(4, 10)
+#undef NF_REG_CASE
+            default: NF_FAIL(NFFTB200_ERR_INVALID, "register-stencil kernels need m <= 4");
+        }
         const int nsc = ((g.T[0] + 3) / 4) * ((g.T[1] + 3) / 4) * ((g.T[2] + 1) / 2);
-        const size_t smem = reg_smem_bytes(g, nsc);
+        const size_t smem = reg_smem_bytes(g, nsc, win_floats);
         if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
         NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (int k0 = 0; k0 < g.K; ++k0) {

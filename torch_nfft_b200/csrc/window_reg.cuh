@@ -64,9 +64,9 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #endif
 }
 
-inline size_t reg_smem_bytes(const Geom& g, int nsc) {
+inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
     // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
-    return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * RegCfg<10, 4, 4, 2>::WIN_FLOATS * 4 +
+    return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * win_floats * 4 +
            (size_t)(2 * nsc + 4) * 4 + (size_t)kRegMaxPts + 64;
 }
 
