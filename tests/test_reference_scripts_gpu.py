@@ -196,3 +196,19 @@ def test_fastsum_with_point_gradients():
         grads.append((x.grad, src.grad, tgt.grad))
     for a, b in zip(*grads):
         assert rel(a, b) < 2e-4
+
+
+def test_raw_operator_surface():
+    """torch.ops.<ns>.nfft_* with the reference's schemas and (pos, x, ...) argument order
+    (reference csrc/core.cpp:43-121); registered under a private namespace here."""
+    ops = torch_nfft.register_torch_ops("torch_nfft_b200_test")
+    torch.manual_seed(7)
+    pos = torch.rand((300, 2), device="cuda") - 0.5
+    x = torch.randn((300, 2), device="cuda")
+    y = ops.nfft_adjoint(pos, x, None, 16, 3, 0)
+    assert rel(y, torch_nfft.nfft_adjoint(x, pos, None, 16, 3)) < 1e-6  # summation order is not run-to-run fixed
+    f = ops.nfft_forward(pos, y, None, 3, 1)
+    assert rel(f, torch_nfft.nfft_forward(y, pos, None, 3, real_output=True)) < 1e-6
+    co = torch_nfft.gaussian_analytic_coeffs(0.2, 2, 16)
+    s = ops.nfft_fastsum(pos, pos, x, co, None, None, 3)
+    assert rel(s, torch_nfft.nfft_fastsum(x, co, pos, cutoff=3)) < 1e-6

@@ -161,12 +161,12 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     const int maxc = d == 3 ? 2 : 8;
     while (ncomp * 2 <= g.K && ncomp * 2 <= maxc) ncomp *= 2;
     if (cplx && ncomp < 2) ncomp = 2;
-    // register-stencil kernels: 3D, m <= 4, real grid, one component per pass
+    // register-stencil kernels: 3D, m <= 4, one float component per pass (complex: re, im passes)
     static const bool no_reg = getenv("NFFTB200_NO_REG") != nullptr;
-    g.use_reg = (d == 3 && m <= 4 && !cplx && !no_reg) ? 1 : 0;
+    g.use_reg = (d == 3 && m <= 4 && !no_reg) ? 1 : 0;
     if (g.use_reg) ncomp = 1;
-    // 2D register-stencil kernels: m = 3 or 4, real grid, up to 8 channels per pass
-    if (d == 2 && (m == 3 || m == 4) && !cplx && !no_reg) g.use_reg = 2;
+    // 2D register-stencil kernels: m = 3 or 4, up to 8 float components per pass
+    if (d == 2 && (m == 3 || m == 4) && !no_reg) g.use_reg = 2;
     g.ncomp = ncomp;
     int T[3] = {1, 1, 1};
     if (d == 1) {

@@ -119,6 +119,28 @@ __device__ __forceinline__ size_t grid_plane(const Geom& g, int b, int k) {
     return g.cplx ? (size_t)((long long)b * g.C + (k >> 1)) * (size_t)g.Md * 2 : (size_t)((long long)b * g.C + k) * (size_t)g.Md;
 }
 
+// One quad (4 consecutive X cells) of component k: real grids are planar (one 16-byte vector
+// reduction / load), complex grids interleave re/im (component k = 2 * channel + part, stride 2).
+__device__ __forceinline__ void reduce_quad(const Geom& g, float* grid, int b, int k, long long cell, float4 val) {
+    if (!g.cplx) {
+        atomicAdd(reinterpret_cast<float4*>(grid + grid_plane(g, b, k) + cell), val);
+    } else {
+        float* p = grid + grid_plane(g, b, k) + 2 * cell + (k & 1);
+        if (val.x != 0.f) atomicAdd(p, val.x);
+        if (val.y != 0.f) atomicAdd(p + 2, val.y);
+        if (val.z != 0.f) atomicAdd(p + 4, val.z);
+        if (val.w != 0.f) atomicAdd(p + 6, val.w);
+    }
+}
+
+__device__ __forceinline__ float4 load_quad(const Geom& g, const float* grid, int b, int k, long long cell) {
+    if (!g.cplx) return __ldg(reinterpret_cast<const float4*>(grid + grid_plane(g, b, k) + cell));
+    const float* p = grid + grid_plane(g, b, k) + 2 * cell;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    return (k & 1) ? make_float4(v0.y, v0.w, v1.y, v1.w) : make_float4(v0.x, v0.z, v1.x, v1.z);
+}
+
 struct TileCtx {
     int b, org[3];
     long long p_lo, p_hi;

@@ -354,10 +354,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     for_each_quad<3>(g, t, [&](int so, long long cell) {
         const float* s = tile + so;
         const float4 val = make_float4(s[0], s[1], s[2], s[3]);
-        if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) {
-            float4* dst = reinterpret_cast<float4*>(a.grid + grid_plane(g, t.b, a.k0) + cell);
-            atomicAdd(dst, val);
-        }
+        if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) reduce_quad(g, a.grid, t.b, a.k0, cell, val);
     });
 }
 
@@ -387,7 +384,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     if (threadIdx.x == 0) s_next = 0;
     // stage the padded tile (periodic wrap resolved per quad)
     for_each_quad<3>(g, t, [&](int so, long long cell) {
-        const float4 val = __ldg(reinterpret_cast<const float4*>(a.grid + grid_plane(g, t.b, a.k0) + cell));
+        const float4 val = load_quad(g, a.grid, t.b, a.k0, cell);
         float* s = tile + so;
         s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
     });

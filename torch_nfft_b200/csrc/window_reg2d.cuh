@@ -285,10 +285,8 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
             if (a.k0 + k < g.K) {
                 const float* s = tile + (size_t)k * g.tile_elems + so;
                 const float4 val = make_float4(s[0], s[1], s[2], s[3]);
-                if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) {
-                    float4* dst = reinterpret_cast<float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell);
-                    atomicAdd(dst, val);
-                }
+                if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f)
+                    reduce_quad(g, a.grid, t.b, a.k0 + k, cell, val);
             }
         }
     });
@@ -323,7 +321,7 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
         for (int k = 0; k < NCOMP; ++k) {
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.k0 + k < g.K) val = __ldg(reinterpret_cast<const float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell));
+            if (a.k0 + k < g.K) val = load_quad(g, a.grid, t.b, a.k0 + k, cell);
             float* s = tile + (size_t)k * g.tile_elems + so;
             s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
         }

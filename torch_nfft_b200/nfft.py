@@ -411,3 +411,32 @@ def nfft_fastsum(x, coeffs, sources, targets=None, source_batch=None, target_bat
         cutoff = m
     return NfftFastsumFunction.apply(x, coeffs, sources, targets, source_batch, target_batch, int(cutoff),
                                      batch_size)
+
+
+# --------------------------------------------------------------------------------------
+# optional: the reference's TorchScript operator surface
+# --------------------------------------------------------------------------------------
+_OPS_REGISTERED = {}
+
+
+def register_torch_ops(namespace: str = "torch_nfft"):
+    """Registers `torch.ops.<namespace>.nfft_adjoint / nfft_forward / nfft_fastsum` with the reference's
+    schemas and argument order (reference csrc/core.cpp:43-121,176-179: `(pos, x, batch, N, m,
+    real_output)`), backed by this engine, for code that calls the raw operators.  The reference
+    registers the same names, so never do this in a process that also loads the reference's core.so.
+    Returns the torch.ops namespace."""
+    if namespace in _OPS_REGISTERED:
+        return getattr(torch.ops, namespace)
+    lib = torch.library.Library(namespace, "DEF")
+    lib.define("nfft_adjoint(Tensor pos, Tensor x, Tensor? batch, int N, int m, int real_output) -> Tensor")
+    lib.define("nfft_forward(Tensor pos, Tensor x, Tensor? batch, int m, int real_output) -> Tensor")
+    lib.define("nfft_fastsum(Tensor sources, Tensor targets, Tensor x, Tensor coeffs, Tensor? source_batch, "
+               "Tensor? target_batch, int m) -> Tensor")
+    lib.impl("nfft_adjoint", lambda pos, x, batch, N, m, real_output: _op_adjoint(pos, x, batch, N, m, bool(real_output)),
+             "CUDA")
+    lib.impl("nfft_forward", lambda pos, x, batch, m, real_output: _op_forward(pos, x, batch, m, bool(real_output)),
+             "CUDA")
+    lib.impl("nfft_fastsum", lambda sources, targets, x, coeffs, sb, tb, m: _op_fastsum(sources, targets, x, coeffs, sb, tb, m),
+             "CUDA")
+    _OPS_REGISTERED[namespace] = lib
+    return getattr(torch.ops, namespace)
