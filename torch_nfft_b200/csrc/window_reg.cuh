@@ -179,10 +179,12 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
         if (pow2) {
             // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
             // rounded, i.e. identical to the reference's double evaluation (:84-86)
-            const float fr = (pm - fl) + (float)g.m;
+            // frac = pm - fl is exact; frac + (m - l) is ONE rounding of the exact value, i.e. bit-identical
+            // to the reference's (float)((double)pos * 2N - shift - l)
+            const float frac = pm - fl;
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
-                const float tt = fr - (float)l;
+                const float tt = frac + (float)(g.m - l);
                 dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
         } else {

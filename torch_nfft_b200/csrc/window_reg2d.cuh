@@ -124,10 +124,10 @@ __device__ __forceinline__ void stage_windows_2d(const Geom& g, const float* s_r
         const float pm = p * (float)g.M;
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
         if (pow2) {
-            const float fr = (pm - fl) + (float)g.m;  // exact, see window_reg.cuh
+            const float frac = pm - fl;  // exact; one rounding per tap below, see window_reg.cuh
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
-                const float tt = fr - (float)l;
+                const float tt = frac + (float)(g.m - l);
                 dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
         } else {
