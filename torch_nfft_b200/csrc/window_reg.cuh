@@ -30,7 +30,8 @@ constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) hel
 #ifndef NFFT_REG_FFMA2
 #define NFFT_REG_FFMA2 1
 #endif
-constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round
+constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round (a power of two <= 32 / 3 lanes... 8)
+static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather reduction needs a power of two; 3 * kRegGroup <= 32");
 #ifndef NFFT_REG_PTUNROLL
 #define NFFT_REG_PTUNROLL 1
 #endif
@@ -137,6 +138,25 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
         }
     }
     __syncthreads();
+}
+
+// Sum NCOMP per-lane values over the warp; afterwards lane l with (l & (32/NCOMP - 1)) == 0 holds the
+// total of channel l / (32/NCOMP) in v[0].  log2(NCOMP) halving exchanges + plain butterflies.
+template <int NCOMP>
+__device__ __forceinline__ void warp_reduce_channels(float (&v)[NCOMP], int lane) {
+    int bit = 16;
+#pragma unroll
+    for (int n = NCOMP; n > 1; n >>= 1, bit >>= 1) {
+        const bool hi = lane & bit;
+#pragma unroll
+        for (int k = 0; k < n / 2; ++k) {
+            const float send = hi ? v[k] : v[k + n / 2];
+            const float keep = hi ? v[k + n / 2] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+#pragma unroll
+    for (; bit > 0; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
 }
 
 // Columns are processed longest first (LPT): with dynamic hand-out the last warp to finish then
@@ -487,17 +507,14 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                     part[gp] = sum.x + sum.y;
                 }
             }
-#pragma unroll
-            for (int gp = 0; gp < kRegGroup; ++gp) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part[gp] += __shfl_xor_sync(0xffffffffu, part[gp], o);
-            }
-            if (lane < npts) {
-                float v = part[0];
-#pragma unroll
-                for (int gp = 1; gp < kRegGroup; ++gp) v = lane == gp ? part[gp] : v;
-                const uint32_t i = (uint32_t)__float_as_int(s_pts[base + lane].w);
-                a.yout[(size_t)i * g.K + a.k0] = v;
+            // sum the kRegGroup partials over the warp (transpose reduction: 9 shuffles for 8 values);
+            // lane 4 p then holds the value of point p of the round
+            warp_reduce_channels<kRegGroup>(part, lane);
+            constexpr int kLanesPerPoint = 32 / kRegGroup;
+            if ((lane & (kLanesPerPoint - 1)) == 0 && lane / kLanesPerPoint < npts) {
+                const int gp = lane / kLanesPerPoint;
+                const uint32_t i = (uint32_t)__float_as_int(s_pts[base + gp].w);
+                a.yout[(size_t)i * g.K + a.k0] = part[0];
             }
             __syncwarp();
         }

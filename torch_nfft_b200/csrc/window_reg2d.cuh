@@ -142,25 +142,6 @@ __device__ __forceinline__ void stage_windows_2d(const Geom& g, const float* s_r
     __syncwarp();
 }
 
-// Sum NCOMP per-lane values over the warp; afterwards lane l with (l & (32/NCOMP - 1)) == 0 holds the
-// total of channel l / (32/NCOMP) in v[0].  log2(NCOMP) halving exchanges + plain butterflies.
-template <int NCOMP>
-__device__ __forceinline__ void warp_reduce_channels(float (&v)[NCOMP], int lane) {
-    int bit = 16;
-#pragma unroll
-    for (int n = NCOMP; n > 1; n >>= 1, bit >>= 1) {
-        const bool hi = lane & bit;
-#pragma unroll
-        for (int k = 0; k < n / 2; ++k) {
-            const float send = hi ? v[k] : v[k + n / 2];
-            const float keep = hi ? v[k + n / 2] : v[k];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-        }
-    }
-#pragma unroll
-    for (; bit > 0; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
-}
-
 // ======================================================================================
 // spread
 // ======================================================================================
