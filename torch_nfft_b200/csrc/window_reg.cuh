@@ -56,6 +56,16 @@ struct RegCfg {
     static constexpr int WIN_FLOATS = (2 * kRegGroup * XYP + 3) / 4 * 4 + kRegGroup * ZWP;
 };
 
+// orders the tile updates of a critical section before the lock release (CTA scope).
+// fence.acq_rel is enough; __threadfence_block() is the sequentially consistent fence.sc.cta.
+__device__ __forceinline__ void release_fence() {
+#ifdef NFFT_REG_SC_FENCE
+    __threadfence_block();
+#else
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
+
 // packed fp32x2 FMA (sm_100 FFMA2): d = a * b + c on both halves
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #if NFFT_REG_FFMA2
@@ -320,7 +330,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                             if (two) dst[g.sZ] = cur[q].y + acc[q][kp].y;
                         }
                     }
-                    __threadfence_block();
+                    release_fence();
                     __syncwarp();
                     if (lane == 0) atomicExch(lk, 0);
                 }

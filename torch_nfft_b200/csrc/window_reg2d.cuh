@@ -250,7 +250,7 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
                 for (int c = 0; c < NCOMP; ++c) bbase[(size_t)c * g.tile_elems + coff[q]] = cur[c] + acc[q][c];
             }
         }
-        __threadfence_block();
+        release_fence();
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
