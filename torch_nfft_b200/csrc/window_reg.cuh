@@ -18,7 +18,10 @@
 
 namespace nfftb200 {
 
-constexpr int kRegThreads = 256;
+#ifndef NFFT_REG_THREADS
+#define NFFT_REG_THREADS 256
+#endif
+constexpr int kRegThreads = NFFT_REG_THREADS;
 constexpr int kRegWarps = kRegThreads / 32;
 #ifndef NFFT_REG_MAXPTS
 #define NFFT_REG_MAXPTS 1536
