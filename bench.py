@@ -78,7 +78,7 @@ class ClockSampler:
         self.rows, self.proc, self.thread = [], None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -279,9 +279,9 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), 0, 0
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started early: nvidia-smi needs ~0.3 s to report
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local) if rank == 0 else None
     _lib.profile_enable(True)
     _lib.profile_read()
     launches0 = _lib.launch_count()
@@ -391,7 +391,16 @@ def run_reference(args):
     # Bounded sample: the reference needs ~23 s per adjoint+forward pair at the full 2^24 points (one
     # global atomic per tap), so a step transforms every `stride`-th point of each point set: same grid
     # (N, m, batch_size, channels), n / stride points.  Its cost is linear in n (fixed costs: < 1 %).
-    stride = max(1, n // args.ref_points)
+    if args.ref_points > 0:
+        ref_points = args.ref_points
+    else:
+        # auto: the largest power-of-two share of the workload that keeps the whole run near 4 minutes
+        # (measured on B200: about 0.85 s fixed + 1.3 us per point per adjoint+forward pair)
+        per_step = 240.0 / max(args.steps + max(args.warmup, 1), 1)
+        ref_points = n
+        while ref_points > 2 ** 18 and 0.85 + 1.31e-6 * ref_points > per_step:
+            ref_points //= 2
+    stride = max(1, n // ref_points)
     if stride > 1:
         pos, x, batch = pos[::stride].contiguous(), x[::stride].contiguous(), batch[::stride].contiguous()
     ns = pos.shape[0]
@@ -429,8 +438,9 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--no-extras", action="store_true", help="development: skip the e2e and cpu_baseline legs")
-    ap.add_argument("--ref-points", type=int, default=2 ** 21,
-                    help="points per step of the reference CUDA arm (bounded sample of the workload)")
+    ap.add_argument("--ref-points", type=int, default=0,
+                    help="points per step of the reference CUDA arm (bounded sample of the workload); 0 = as many "
+                         "as fit a ~4 minute run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
