@@ -643,6 +643,20 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
     return NFFTB200_OK;
 }
 
+#ifdef NFFT_PHASE_TIMING
+// debug build only: out[2][24] = accumulated clock64() phase lengths of the register-stencil kernels
+// (window_reg.cuh); reset = 1 clears the counters afterwards
+int nfftb200_debug_phase_read(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 48) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[48] = {0};
+        cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 void nfftb200_profile_enable(int on) {
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     g_prof_on = on != 0;

@@ -35,10 +35,30 @@ constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) hel
 #endif
 constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round (a power of two <= 32 / 3 lanes... 8)
 static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather reduction needs a power of two; 3 * kRegGroup <= 32");
+#ifndef NFFT_REG_STAGGER
+#define NFFT_REG_STAGGER 0  // measured at c4: 4.61 ms with the staggered sweep, 4.51 ms without
+#endif
 #ifndef NFFT_REG_PTUNROLL
 #define NFFT_REG_PTUNROLL 1
 #endif
 constexpr int kPtUnroll = NFFT_REG_PTUNROLL;  // unroll factor of the spread point loop
+
+// Debug build (-DNFFT_PHASE_TIMING): thread 0 of every CTA adds the clock64() length of its phases to
+// g_phase[kernel][phase]; read back through nfftb200_debug_phase_read.  Phases: 0 zero + bucket +
+// order, 1 column sweep (until this warp is done), 2 wait for the other warps, 3 flush / store,
+// 4 number of CTAs.
+#ifdef NFFT_PHASE_TIMING
+__device__ unsigned long long g_phase[2][24];  // [8 + w]: sweep length of warp w
+#define NFFT_PHASE_MARK(var) const long long var = clock64()
+#define NFFT_PHASE_ADD(kern, ph, t0, t1) \
+    if (threadIdx.x == 0) atomicAdd(&g_phase[kern][ph], (unsigned long long)((t1) - (t0)))
+#define NFFT_PHASE_WARP(kern, t0) \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[kern][8 + (threadIdx.x >> 5)], (unsigned long long)(clock64() - (t0)))
+#else
+#define NFFT_PHASE_MARK(var)
+#define NFFT_PHASE_ADD(kern, ph, t0, t1)
+#define NFFT_PHASE_WARP(kern, t0)
+#endif
 
 template <int LC, int SX, int SY, int SZ>
 struct RegCfg {
@@ -98,6 +118,8 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
     // tile-local cell 0 in wrapped grid coordinates
     const int lo0 = t.org[0] + g.org[0], lo1 = t.org[1] + g.org[1], lo2 = t.org[2] + g.org[2];
     const float Mf = (float)g.M;
+    // (Issuing all index loads, then all position loads, before the first use was measured and is
+    // slower: this phase overlaps the other resident CTA's sweep, see DESIGN.md.)
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         const int e = threadIdx.x + k * kRegThreads;
@@ -243,6 +265,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
+    NFFT_PHASE_MARK(ph0);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
@@ -260,10 +283,16 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
+    NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    NFFT_PHASE_MARK(phb);
     __shared__ int s_order[64];
     order_columns(s_start, nsx * nsy, nsz, s_order);
+    NFFT_PHASE_MARK(ph1);
+    NFFT_PHASE_ADD(0, 5, ph0, pha);
+    NFFT_PHASE_ADD(0, 6, pha, phb);
+    NFFT_PHASE_ADD(0, 7, phb, ph1);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = s_win + warp * Cfg::WIN_FLOATS;
@@ -345,45 +374,71 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
             }
         };
 
-        // the column's points are staged in rounds of kRegGroup regardless of supercell boundaries
-        const int lo_col = s_start[c0], hi_col = s_start[c0 + nsz];
-        int scz = 0, next_end = s_start[c0 + 1];
-        for (int base = lo_col; base < hi_col; base += kRegGroup) {
-            const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
-            stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
-            const float* wv = win;          // x / y windows of the point
-            const float* wzp = win + kXY;   // z window of the point
-#pragma unroll kPtUnroll
-            for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
-                while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
-                    advance(scz, false);
-                    ++scz;
-                    next_end = s_start[c0 + scz + 1];
-                }
-                const float xval = s_pts[base + gp].w;
-                float2 wz[ZP];
-#pragma unroll
-                for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                    const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
-                    wz[2 * l4] = make_float2(w4.x, w4.y);
-                    wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                }
-                float v[CPL];
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[wj[q]]) * wv[wi[q]];
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) {
-                    const float2 vv = make_float2(v[q], v[q]);
-#pragma unroll
-                    for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
-                }
+        // Optionally (NFFT_REG_STAGGER) every warp starts its sweep at a different height and wraps
+        // around (two segments), so that warps do not meet at the same plane lock; the second full
+        // add-out costs more than the lock waits it removes, so the default is one segment from z = 0.
+        // Within a segment the points are staged in rounds of kRegGroup regardless of supercell
+        // boundaries.
+#if NFFT_REG_STAGGER
+        const int z0 = (warp * nsz) / kRegWarps;
+#else
+        const int z0 = 0;
+#endif
+        for (int seg = 0; seg < 2; ++seg) {
+            const int zb = seg == 0 ? z0 : 0, ze = seg == 0 ? nsz : z0;
+            if (zb >= ze) continue;
+            const int lo_seg = s_start[c0 + zb], hi_seg = s_start[c0 + ze];
+            if (lo_seg == hi_seg) continue;  // acc is all zero: nothing to add out
+            int scz = zb, next_end = s_start[c0 + zb + 1];
+            while (next_end == lo_seg) {  // leading empty supercells: the block is still zero
+                ++scz;
+                next_end = s_start[c0 + scz + 1];
             }
-            __syncwarp();
+            for (int base = lo_seg; base < hi_seg; base += kRegGroup) {
+                const int npts = hi_seg - base < kRegGroup ? hi_seg - base : kRegGroup;
+                stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
+                const float* wv = win;          // x / y windows of the point
+                const float* wzp = win + kXY;   // z window of the point
+#pragma unroll kPtUnroll
+                for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
+                    while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
+                        advance(scz, false);
+                        ++scz;
+                        next_end = s_start[c0 + scz + 1];
+                    }
+                    const float xval = s_pts[base + gp].w;
+                    float2 wz[ZP];
+#pragma unroll
+                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                        const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
+                        wz[2 * l4] = make_float2(w4.x, w4.y);
+                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
+                    }
+                    float v[CPL];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[wj[q]]) * wv[wi[q]];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const float2 vv = make_float2(v[q], v[q]);
+#pragma unroll
+                        for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
+                    }
+                }
+                __syncwarp();
+            }
+            // the segment's last point lies in supercell scz: everything the block holds goes out and
+            // the block is zero again
+            advance(scz, true);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q)
+#pragma unroll
+                for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = make_float2(0.f, 0.f);
         }
-        for (; scz < nsz - 1; ++scz) advance(scz, false);
-        advance(nsz - 1, true);
     }
+    NFFT_PHASE_WARP(0, ph1);
+    NFFT_PHASE_MARK(ph2);
     __syncthreads();
+    NFFT_PHASE_MARK(ph3);
 
     // flush: vector reductions into the global grid; untouched (== 0) quads are skipped
     for_each_quad<3>(g, t, [&](int so, long long cell) {
@@ -391,6 +446,12 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         const float4 val = make_float4(s[0], s[1], s[2], s[3]);
         if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) reduce_quad(g, a.grid, t.b, a.k0, cell, val);
     });
+    NFFT_PHASE_MARK(ph4);
+    NFFT_PHASE_ADD(0, 0, ph0, ph1);
+    NFFT_PHASE_ADD(0, 1, ph1, ph2);
+    NFFT_PHASE_ADD(0, 2, ph2, ph3);
+    NFFT_PHASE_ADD(0, 3, ph3, ph4);
+    NFFT_PHASE_ADD(0, 4, 0, 1);
 }
 
 // ======================================================================================
@@ -404,6 +465,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
+    NFFT_PHASE_MARK(ph0);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
@@ -424,10 +486,16 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
     });
     __syncthreads();
+    NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    NFFT_PHASE_MARK(phb);
     __shared__ int s_order[64];
     order_columns(s_start, nsx * nsy, nsz, s_order);
+    NFFT_PHASE_MARK(ph1);
+    NFFT_PHASE_ADD(1, 5, ph0, pha);
+    NFFT_PHASE_ADD(1, 6, pha, phb);
+    NFFT_PHASE_ADD(1, 7, phb, ph1);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = s_win + warp * Cfg::WIN_FLOATS;
@@ -533,6 +601,16 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         }
     }
     (void)WZ;
+    NFFT_PHASE_WARP(1, ph1);
+    NFFT_PHASE_MARK(ph2);
+#ifdef NFFT_PHASE_TIMING
+    __syncthreads();
+#endif
+    NFFT_PHASE_MARK(ph3);
+    NFFT_PHASE_ADD(1, 0, ph0, ph1);
+    NFFT_PHASE_ADD(1, 1, ph1, ph2);
+    NFFT_PHASE_ADD(1, 2, ph2, ph3);
+    NFFT_PHASE_ADD(1, 4, 0, 1);
 }
 
 }  // namespace nfftb200
