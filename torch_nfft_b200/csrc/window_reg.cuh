@@ -239,7 +239,7 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
             const float frac = pm - fl;
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
-                const float tt = frac + (float)(g.m - l);
+                const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
                 dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
         } else {

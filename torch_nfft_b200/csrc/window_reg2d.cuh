@@ -127,7 +127,7 @@ __device__ __forceinline__ void stage_windows_2d(const Geom& g, const float* s_r
             const float frac = pm - fl;  // exact; one rounding per tap below, see window_reg.cuh
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
-                const float tt = frac + (float)(g.m - l);
+                const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
                 dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
         } else {
