@@ -38,6 +38,9 @@ static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather re
 #ifndef NFFT_REG_STAGGER
 #define NFFT_REG_STAGGER 0  // measured at c4: 4.61 ms with the staggered sweep, 4.51 ms without
 #endif
+#ifndef NFFT_REG_SCALEZ
+#define NFFT_REG_SCALEZ 1
+#endif
 #ifndef NFFT_REG_PTUNROLL
 #define NFFT_REG_PTUNROLL 1
 #endif
@@ -212,7 +215,8 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
 // Phase A of a warp round: the taps of up to kRegGroup points are evaluated and stored at their
 // shifted positions inside zero-initialised windows.  Lane <-> (point, dimension): each lane runs
 // L independent expf chains (unrolled), so the latency of one tap hides behind the others.
-template <typename Cfg, int LC>
+// SCALE_Z: the z taps carry the point's value (spread), so the sweep multiplies only psi(Y) * psi(X).
+template <typename Cfg, int LC, bool SCALE_Z = false>
 __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
                                               int npts, float* win, int lane, bool pow2) {
     constexpr int kQuads = Cfg::WIN_FLOATS / 4;
@@ -231,6 +235,8 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
         float* dst = slot == 2 ? win + kXY + pt * Cfg::ZWP + off : win + (2 * pt + slot) * Cfg::XYP + off;
         const float pm = p * (float)g.M;
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
+        float amp = g.inv_sqrt_b_pi;
+        if (SCALE_Z && slot == 2) amp *= s_pts[base + pt].w;
         if (pow2) {
             // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
             // rounded, i.e. identical to the reference's double evaluation (:84-86)
@@ -240,14 +246,14 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
-                dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+                dst[l] = expf(-(tt * tt) * g.inv_b) * amp;  // eval_phi, :24-28
             }
         } else {
             const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = (float)(bd - (double)l);
-                dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;
+                dst[l] = expf(-(tt * tt) * g.inv_b) * amp;
             }
         }
     }
@@ -396,7 +402,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
             }
             for (int base = lo_seg; base < hi_seg; base += kRegGroup) {
                 const int npts = hi_seg - base < kRegGroup ? hi_seg - base : kRegGroup;
-                stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
+                stage_windows<Cfg, LC, NFFT_REG_SCALEZ>(g, s_pts, s_off, base, npts, win, lane, pow2);
                 const float* wv = win;          // x / y windows of the point
                 const float* wzp = win + kXY;   // z window of the point
 #pragma unroll kPtUnroll
@@ -406,7 +412,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                         ++scz;
                         next_end = s_start[c0 + scz + 1];
                     }
+#if !NFFT_REG_SCALEZ
                     const float xval = s_pts[base + gp].w;
+#endif
                     float2 wz[ZP];
 #pragma unroll
                     for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
@@ -416,7 +424,11 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     }
                     float v[CPL];
 #pragma unroll
+#if NFFT_REG_SCALEZ
+                    for (int q = 0; q < CPL; ++q) v[q] = wv[wj[q]] * wv[wi[q]];  // x value folded into wz
+#else
                     for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[wj[q]]) * wv[wi[q]];
+#endif
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
                         const float2 vv = make_float2(v[q], v[q]);
