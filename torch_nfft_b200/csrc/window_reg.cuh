@@ -41,6 +41,9 @@ static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather re
 #ifndef NFFT_REG_SCALEZ
 #define NFFT_REG_SCALEZ 1
 #endif
+#ifndef NFFT_REG_GATHER_ORDER
+#define NFFT_REG_GATHER_ORDER 1
+#endif
 #ifndef NFFT_REG_PTUNROLL
 #define NFFT_REG_PTUNROLL 1
 #endif
@@ -588,6 +591,23 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                         wz[2 * l4] = make_float2(w4.x, w4.y);
                         wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
                     }
+#if NFFT_REG_GATHER_ORDER
+                    // sum over the (x, y) positions first (scalar-broadcast FFMA2, ZP independent
+                    // chains), then over z
+                    float2 zsum[ZP];
+#pragma unroll
+                    for (int kp = 0; kp < ZP; ++kp) zsum[kp] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const float w = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X)
+                        const float2 ww = make_float2(w, w);
+#pragma unroll
+                        for (int kp = 0; kp < ZP; ++kp) zsum[kp] = ffma2(ww, blk[q][kp], zsum[kp]);
+                    }
+                    float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int kp = 0; kp < ZP; ++kp) sum = ffma2(wz[kp], zsum[kp], sum);
+#else
                     float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
@@ -597,6 +617,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                         for (int kp = 0; kp < ZP; ++kp) inner = ffma2(wz[kp], blk[q][kp], inner);
                         sum = ffma2(make_float2(w, w), inner, sum);
                     }
+#endif
                     part[gp] = sum.x + sum.y;
                 }
             }
