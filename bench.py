@@ -167,6 +167,42 @@ def cpu_baseline_ndft(workload, sample_points=192):
 
 
 # ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads to the NUMA node of its GPU, so the pinned staging buffers of the
+    end-to-end arm are allocated next to the PCIe root the GPU hangs off (matters at 8 ranks per box:
+    remote-node staging halves the copy bandwidth).  Returns the node or None when it cannot be found."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id  # older torch: attribute missing
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            import subprocess
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+        if isinstance(bus, int):
+            return None
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -178,6 +214,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local)   # before any pinned allocation: first touch decides the node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     d, N, m, n, B, C, distribution = WORKLOADS[args.workload]
@@ -334,7 +371,8 @@ def run_ours(args):
                            (n * (4 * d + 4 * C + 8)) >> 20, (B * C * (2 * N) ** d * 4) >> 20)},
             "e2e": {"value": n * world / (ms_e2e / args.steps * 1e-3), "unit": "points/s",
                     "h2d_bytes_per_step": n * (4 * d + 4 * C + 8),
-                    "d2h_bytes_per_step": B * C * N ** d * 8 + n * C * 4},
+                    "d2h_bytes_per_step": B * C * N ** d * 8 + n * C * 4,
+                    "host_numa_node_rank0": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "spread kernel (adjoint window convolution; spread_reg_kernel at c4)",
