@@ -38,4 +38,7 @@ for k, kern in enumerate(("spread", "gather")):
         v[0] / ctas, v[1] / ctas, v[2] / ctas, v[3] / ctas, tot / ctas),
         "shares: " + " ".join("%.1f%%" % (100.0 * a / max(tot, 1)) for a in v[:4]),
         "| sweep length by warp: " + " ".join("%.0f" % (a / ctas) for a in v[8:16]),
+        "| longest CTA %d cycles, kernel span %.3f ms, slot occupancy %.1f%% (2 CTAs x 148 SMs at 1.965 GHz), CTAs by fill quartile %s" % (
+            v[16], (v[18] - ((~v[17]) & (2 ** 64 - 1))) * 1e-6,
+            100.0 * tot / (296 * 1.965e9 * max((v[18] - ((~v[17]) & (2 ** 64 - 1))) * 1e-9, 1e-12)), v[19:23]),
         "| setup split: zero/tile-load %.0f bucket %.0f order %.0f" % (v[5] / ctas, v[6] / ctas, v[7] / ctas))

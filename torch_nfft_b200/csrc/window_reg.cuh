@@ -35,9 +35,6 @@ constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) hel
 #endif
 constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round (a power of two <= 32 / 3 lanes... 8)
 static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather reduction needs a power of two; 3 * kRegGroup <= 32");
-#ifndef NFFT_REG_STAGGER
-#define NFFT_REG_STAGGER 0  // measured at c4: 4.61 ms with the staggered sweep, 4.51 ms without
-#endif
 #ifndef NFFT_REG_SCALEZ
 #define NFFT_REG_SCALEZ 1
 #endif
@@ -60,10 +57,27 @@ __device__ unsigned long long g_phase[2][24];  // [8 + w]: sweep length of warp 
     if (threadIdx.x == 0) atomicAdd(&g_phase[kern][ph], (unsigned long long)((t1) - (t0)))
 #define NFFT_PHASE_WARP(kern, t0) \
     if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[kern][8 + (threadIdx.x >> 5)], (unsigned long long)(clock64() - (t0)))
+// [16] longest CTA (cycles), [17] / [18] first CTA start / last CTA end (globaltimer ns, [17] stored negated
+// so that a zeroed counter works with atomicMax), [19..22] CTAs by points: <= 1/4, 1/2, 3/4, 1 of kRegMaxPts
+__device__ __forceinline__ unsigned long long phase_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NFFT_PHASE_BEGIN(kern) \
+    if (threadIdx.x == 0) atomicMax(&g_phase[kern][17], ~phase_ns())
+#define NFFT_PHASE_END(kern, t0, t1, cnt)                                                  \
+    if (threadIdx.x == 0) {                                                                \
+        atomicMax(&g_phase[kern][16], (unsigned long long)((t1) - (t0)));                  \
+        atomicMax(&g_phase[kern][18], phase_ns());                                         \
+        atomicAdd(&g_phase[kern][19 + min(3, (int)((cnt) * 4 / (kRegMaxPts + 1)))], 1ull); \
+    }
 #else
 #define NFFT_PHASE_MARK(var)
 #define NFFT_PHASE_ADD(kern, ph, t0, t1)
 #define NFFT_PHASE_WARP(kern, t0)
+#define NFFT_PHASE_BEGIN(kern)
+#define NFFT_PHASE_END(kern, t0, t1, cnt)
 #endif
 
 template <int LC, int SX, int SY, int SZ>
@@ -215,6 +229,55 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
     __syncthreads();
 }
 
+// Work units of the 3D sweep: a column of supercells, or - when a column holds more than 1.5x the
+// average (clustered points) - up to 4 z-ranges of it with about equal point counts, so that one heavy
+// column does not leave the other warps of the CTA idle.  Unit = col | zb << 8 | ze << 16 (supercells
+// [zb, ze)); s_units[rank] is ordered longest first (LPT), *s_nunits counts the non-empty units (<= 64)
+// and must have been zeroed before the caller's last barrier.
+#ifndef NFFT_REG_SPLIT
+#define NFFT_REG_SPLIT 1
+#endif
+__device__ __forceinline__ void make_units(const int* s_start, int ncols, int nsz, int* s_units, int* s_nunits) {
+    __shared__ int s_raw[64], s_rawcnt[64];
+    const int total = s_start[ncols * nsz] - s_start[0];
+    const int maxseg = NFFT_REG_SPLIT ? (64 / ncols < 4 ? 64 / ncols : 4) : 1;
+    if ((int)threadIdx.x < ncols) {
+        const int c0 = threadIdx.x * nsz;
+        const int lo = s_start[c0], cnt = s_start[c0 + nsz] - lo;
+        int nseg = 1;
+        if (2 * cnt * ncols > 3 * total) nseg = (2 * cnt * ncols + 3 * total - 1) / (3 * total);  // ceil(cnt / 1.5 avg)
+        nseg = nseg < maxseg ? nseg : maxseg;
+        int zb = 0;
+        for (int j = 1; j <= nseg && cnt > 0; ++j) {
+            int ze = nsz;
+            if (j < nseg) {
+                const int target = lo + (int)((long long)cnt * j / nseg);
+                ze = zb;
+                while (ze < nsz && s_start[c0 + ze] < target) ++ze;  // first boundary at or above the target
+            }
+            const int ucnt = s_start[c0 + ze] - s_start[c0 + zb];
+            if (ucnt > 0) {
+                const int k = atomicAdd(s_nunits, 1);
+                s_raw[k] = (int)threadIdx.x | zb << 8 | ze << 16;
+                s_rawcnt[k] = ucnt;
+                zb = ze;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = *s_nunits;
+    if ((int)threadIdx.x < n) {
+        const int cnt = s_rawcnt[threadIdx.x];
+        int rank = 0;
+        for (int o = 0; o < n; ++o) {
+            const int oc = s_rawcnt[o];
+            rank += (oc > cnt || (oc == cnt && o < (int)threadIdx.x)) ? 1 : 0;
+        }
+        s_units[rank] = s_raw[threadIdx.x];
+    }
+    __syncthreads();
+}
+
 // Phase A of a warp round: the taps of up to kRegGroup points are evaluated and stored at their
 // shifted positions inside zero-initialised windows.  Lane <-> (point, dimension): each lane runs
 // L independent expf chains (unrolled), so the latency of one tap hides behind the others.
@@ -275,6 +338,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     TileCtx t;
     if (!decode_item(g, a, t)) return;
     NFFT_PHASE_MARK(ph0);
+    NFFT_PHASE_BEGIN(0);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
@@ -290,14 +354,14 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 
     for (int i = threadIdx.x; i < g.tile_elems; i += kRegThreads) tile[i] = 0.f;
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    if (threadIdx.x == 0) s_next = 0;
+    __shared__ int s_order[64], s_nunits;
+    if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     __syncthreads();
     NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-    __shared__ int s_order[64];
-    order_columns(s_start, nsx * nsy, nsz, s_order);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(0, 5, ph0, pha);
     NFFT_PHASE_ADD(0, 6, pha, phb);
@@ -320,15 +384,17 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
 
-    // columns of supercells are handed out dynamically, one per warp
+    // work units (columns of supercells or z-ranges of heavy columns) are handed out dynamically
+    const int nunits = s_nunits;
     for (;;) {
         int col = 0;
         if (lane == 0) col = atomicAdd(&s_next, 1);
         col = __shfl_sync(0xffffffffu, col, 0);
-        if (col >= nsx * nsy) break;
-        col = s_order[col];
+        if (col >= nunits) break;
+        const int unit = s_order[col];
+        col = unit & 0xff;
+        const int zb = (unit >> 8) & 0xff, ze = unit >> 16;
         const int c0 = col * nsz;
-        if (s_start[c0] == s_start[c0 + nsz]) break;  // columns are ordered by size: the rest is empty
         const int scx = col % nsx, scy = col / nsx;
         float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
 
@@ -383,21 +449,10 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
             }
         };
 
-        // Optionally (NFFT_REG_STAGGER) every warp starts its sweep at a different height and wraps
-        // around (two segments), so that warps do not meet at the same plane lock; the second full
-        // add-out costs more than the lock waits it removes, so the default is one segment from z = 0.
-        // Within a segment the points are staged in rounds of kRegGroup regardless of supercell
+        // Within the unit the points are staged in rounds of kRegGroup regardless of supercell
         // boundaries.
-#if NFFT_REG_STAGGER
-        const int z0 = (warp * nsz) / kRegWarps;
-#else
-        const int z0 = 0;
-#endif
-        for (int seg = 0; seg < 2; ++seg) {
-            const int zb = seg == 0 ? z0 : 0, ze = seg == 0 ? nsz : z0;
-            if (zb >= ze) continue;
-            const int lo_seg = s_start[c0 + zb], hi_seg = s_start[c0 + ze];
-            if (lo_seg == hi_seg) continue;  // acc is all zero: nothing to add out
+        {
+            const int lo_seg = s_start[c0 + zb], hi_seg = s_start[c0 + ze];  // never empty
             int scz = zb, next_end = s_start[c0 + zb + 1];
             while (next_end == lo_seg) {  // leading empty supercells: the block is still zero
                 ++scz;
@@ -441,13 +496,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                 }
                 __syncwarp();
             }
-            // the segment's last point lies in supercell scz: everything the block holds goes out and
-            // the block is zero again
+            // the unit's last point lies in supercell scz: everything the block holds goes out
             advance(scz, true);
-#pragma unroll
-            for (int q = 0; q < CPL; ++q)
-#pragma unroll
-                for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = make_float2(0.f, 0.f);
         }
     }
     NFFT_PHASE_WARP(0, ph1);
@@ -467,6 +517,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     NFFT_PHASE_ADD(0, 2, ph2, ph3);
     NFFT_PHASE_ADD(0, 3, ph3, ph4);
     NFFT_PHASE_ADD(0, 4, 0, 1);
+    NFFT_PHASE_END(0, ph0, ph4, cnt);
 }
 
 // ======================================================================================
@@ -481,6 +532,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     TileCtx t;
     if (!decode_item(g, a, t)) return;
     NFFT_PHASE_MARK(ph0);
+    NFFT_PHASE_BEGIN(1);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
@@ -493,7 +545,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     __shared__ int s_next;
 
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    if (threadIdx.x == 0) s_next = 0;
+    __shared__ int s_order[64], s_nunits;
+    if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     // stage the padded tile (periodic wrap resolved per quad)
     for_each_quad<3>(g, t, [&](int so, long long cell) {
         const float4 val = load_quad(g, a.grid, t.b, a.k0, cell);
@@ -505,8 +558,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-    __shared__ int s_order[64];
-    order_columns(s_start, nsx * nsy, nsz, s_order);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(1, 5, ph0, pha);
     NFFT_PHASE_ADD(1, 6, pha, phb);
@@ -529,24 +581,34 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
     const int zmax = g.P[2] - 1;
 
+    const int nunits = s_nunits;
     for (;;) {
         int col = 0;
         if (lane == 0) col = atomicAdd(&s_next, 1);
         col = __shfl_sync(0xffffffffu, col, 0);
-        if (col >= nsx * nsy) break;
-        col = s_order[col];
+        if (col >= nunits) break;
+        const int unit = s_order[col];
+        col = unit & 0xff;
+        const int zb0 = (unit >> 8) & 0xff, ze0 = unit >> 16;
         const int c0 = col * nsz;
-        if (s_start[c0] == s_start[c0 + nsz]) break;
         const int scx = col % nsx, scy = col / nsx;
         const float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
+        const int lo_col = s_start[c0 + zb0], hi_col = s_start[c0 + ze0];  // never empty
+        int scz = zb0, next_end = s_start[c0 + zb0 + 1];
+        while (next_end == lo_col) {  // leading empty supercells
+            ++scz;
+            next_end = s_start[c0 + scz + 1];
+        }
 
-        // register block: planes [scz*SZ, scz*SZ + 2 ZP) of the column; loaded for scz = 0, then slid
+        // register block: planes [scz*SZ, scz*SZ + 2 ZP) of the column; loaded at the unit's first
+        // populated supercell, then slid
         float2 blk[CPL][ZP];
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) {
-                const int za = 2 * kp < zmax ? 2 * kp : zmax, zb = 2 * kp + 1 < zmax ? 2 * kp + 1 : zmax;
+                const int z0 = scz * SZ + 2 * kp;
+                const int za = z0 < zmax ? z0 : zmax, zb = z0 + 1 < zmax ? z0 + 1 : zmax;
                 blk[q][kp] = make_float2(cbase[za * g.sZ + coff[q]], cbase[zb * g.sZ + coff[q]]);
             }
         // move the block to supercell `scz`: slide down by SZ and load the SZ new top planes
@@ -566,8 +628,6 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
             }
         };
 
-        const int lo_col = s_start[c0], hi_col = s_start[c0 + nsz];
-        int scz = 0, next_end = s_start[c0 + 1];
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
             stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
@@ -644,6 +704,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     NFFT_PHASE_ADD(1, 1, ph1, ph2);
     NFFT_PHASE_ADD(1, 2, ph2, ph3);
     NFFT_PHASE_ADD(1, 4, 0, 1);
+    NFFT_PHASE_END(1, ph0, ph3, cnt);
 }
 
 }  // namespace nfftb200
