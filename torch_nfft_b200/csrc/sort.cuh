@@ -127,21 +127,46 @@ __device__ __forceinline__ int wrap_mod(int v, int M) {
 }
 
 // key = ((b*nt[2] + tz)*nt[1] + ty)*nt[0] + tx, tile index from the wrapped reference cell.
+// Powers of two (the usual M and tile edges) take mask / shift paths: the generic integer modulo and
+// division cost ~25 instructions each, six per point.
+struct KeyFast {
+    bool m_pow2;
+    int tshift[3];  // log2(T[slot]) or -1
+};
+
+__device__ __forceinline__ KeyFast key_fast(const Geom& g) {
+    KeyFast f;
+    f.m_pow2 = (g.M & (g.M - 1)) == 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) f.tshift[s] = (g.T[s] & (g.T[s] - 1)) == 0 ? __ffs(g.T[s]) - 1 : -1;
+    return f;
+}
+
+__device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, const int64_t* __restrict__ batch,
+                                              long long i, const Geom& g, const KeyFast& f) {
+    long long b = batch ? batch[i] : 0;
+    b = b < 0 ? 0 : (b >= g.B ? g.B - 1 : b);
+    uint32_t key = (uint32_t)b;
+    const float Mf = (float)g.M;
+    const float* p = pos + i * g.dim;
+#pragma unroll
+    for (int slot = 2; slot >= 0; --slot) {
+        if (slot < g.dim) {
+            const int c = (int)floorf(p[g.dim - 1 - slot] * Mf);  // spatial_window_operations.cu:50
+            const int cw = f.m_pow2 ? (c & (g.M - 1)) : wrap_mod(c, g.M);
+            const int tile = f.tshift[slot] >= 0 ? (cw >> f.tshift[slot]) : cw / g.T[slot];
+            key = key * (uint32_t)g.nt[slot] + (uint32_t)tile;
+        }
+    }
+    return key;
+}
+
 __global__ void __launch_bounds__(256)
 key_hist_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, long long n, Geom g,
                 uint32_t* __restrict__ keys, uint32_t* __restrict__ bin_count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    long long b = batch ? batch[i] : 0;
-    b = b < 0 ? 0 : (b >= g.B ? g.B - 1 : b);
-    uint32_t key = (uint32_t)b;
-    const float Mf = (float)g.M;
-    for (int slot = g.dim - 1; slot >= 0; --slot) {
-        const int a = g.dim - 1 - slot;
-        int c = (int)floorf(pos[i * g.dim + a] * Mf);  // spatial_window_operations.cu:50
-        int cw = wrap_mod(c, g.M);
-        key = key * (uint32_t)g.nt[slot] + (uint32_t)(cw / g.T[slot]);
-    }
+    const uint32_t key = point_key(pos, batch, i, g, key_fast(g));
     keys[i] = key;
     if (bin_count) atomicAdd(&bin_count[key], 1u);  // only when no radix pass follows (single bin)
 }
@@ -167,6 +192,9 @@ count_sorted_kernel(const uint32_t* __restrict__ keys_sorted, long long n, uint3
 }
 
 // ------------------------------------------------------------------------- stable radix sort
+#ifndef NFFT_SORT_MINB
+#define NFFT_SORT_MINB 5  // resident CTAs per SM the scatter kernel is compiled for (register cap)
+#endif
 constexpr int kRsThreads = 256;
 constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsIpt = 16;  // items per thread
@@ -189,13 +217,36 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uin
     table[(long long)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
+// Keys of one radix tile and, in the same pass, the tile's row of the first radix pass's digit table
+// (saves re-reading the keys in radix_hist_kernel).
+__global__ void __launch_bounds__(kRsThreads)
+key_tile_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, long long n, Geom g,
+                uint32_t* __restrict__ keys, uint32_t* __restrict__ table, int nblocks) {
+    __shared__ uint32_t hist[kRsBins];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const KeyFast f = key_fast(g);
+    const long long base = (long long)blockIdx.x * kRsTile;
+#pragma unroll 4
+    for (int k = 0; k < kRsIpt; ++k) {
+        const long long i = base + (long long)k * kRsThreads + threadIdx.x;
+        if (i < n) {
+            const uint32_t key = point_key(pos, batch, i, g, f);
+            keys[i] = key;
+            atomicAdd(&hist[key & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    table[(long long)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
 // In-order scatter.  Warp w of a block owns the contiguous items [base + w*512, +512) and walks
 // them 32 at a time, so (block, warp, round, lane) order == input order and equal digits keep
 // their relative order (stable).  idx_in == nullptr means the identity payload.
 // The block first sorts its 4096 items by digit in shared memory and then writes them out in that
 // order, so consecutive threads store to consecutive addresses of each digit's run (full sectors
 // instead of one 4-byte store per 32-byte sector).
-__global__ void __launch_bounds__(kRsThreads)
+__global__ void __launch_bounds__(kRsThreads, NFFT_SORT_MINB)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, long long n, int shift,
                      const uint32_t* __restrict__ table_scanned, int nblocks) {
@@ -211,14 +262,15 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
     const long long blk = (long long)blockIdx.x * kRsTile;
     const long long base = blk + (long long)warp * (32 * kRsIpt);
-    uint32_t key[kRsIpt];
+    // the keys are read again in the second phase (L2 hits) instead of being held in 16 more registers:
+    // the kernel is latency-bound and 5 resident CTAs per SM beat 2
     uint32_t rank[kRsIpt];
 #pragma unroll
     for (int s = 0; s < kRsIpt; ++s) {
         const long long i = base + s * 32 + lane;
         const bool valid = i < n;
-        key[s] = valid ? keys_in[i] : 0xffffffffu;
-        const uint32_t digit = valid ? ((key[s] >> shift) & 255u) : 256u;
+        const uint32_t key = valid ? keys_in[i] : 0xffffffffu;
+        const uint32_t digit = valid ? ((key >> shift) & 255u) : 256u;
         const uint32_t mask = __match_any_sync(0xffffffffu, digit);
         const int leader = __ffs(mask) - 1;
         uint32_t old = 0;
@@ -251,9 +303,10 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     for (int s = 0; s < kRsIpt; ++s) {
         const long long i = base + s * 32 + lane;
         if (i < n) {
-            const uint32_t digit = (key[s] >> shift) & 255u;
+            const uint32_t key = keys_in[i];
+            const uint32_t digit = (key >> shift) & 255u;
             const uint32_t lp = s_loc[digit] + wcnt[warp][digit] + rank[s];
-            s_key[lp] = key[s];
+            s_key[lp] = key;
             s_idx[lp] = idx_in ? idx_in[i] : (uint32_t)i;
         }
     }
@@ -378,16 +431,20 @@ inline int sort_points(const float* pos, const int64_t* batch, long long n, cons
     const uint32_t* kin = keys0;
     const uint32_t* iin = nullptr;  // identity payload on the first pass
     if (n > 0) {
-        NF_LAUNCH(key_hist_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pos, batch, n, g, keys0,
-                  passes == 0 ? bin_count : (uint32_t*)nullptr);
         if (passes == 0) {
+            NF_LAUNCH(key_hist_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pos, batch, n, g, keys0, bin_count);
             NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, ibuf[0], n);
+        } else {
+            NF_LAUNCH(key_tile_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, pos, batch, n, g, keys0, table,
+                      (int)L.nblocks);
         }
         for (int p = 0; p < passes; ++p) {
             uint32_t* kout = kbuf[p & 1];
             uint32_t* iout = ibuf[p & 1];
-            NF_LAUNCH(radix_hist_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, n, 8 * p, table,
-                      (int)L.nblocks);
+            if (p > 0) {
+                NF_LAUNCH(radix_hist_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, n, 8 * p, table,
+                          (int)L.nblocks);
+            }
             NF_TRY(scan_exclusive(table, table, kRsBins * L.nblocks, scan, st));
             NF_LAUNCH(radix_scatter_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, iin, kout, iout, n, 8 * p,
                       table, (int)L.nblocks);
