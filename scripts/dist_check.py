@@ -29,9 +29,21 @@ s = D.nfft_fastsum_point_sharded(x[lo:hi], co, pos[lo:hi] * 0.5, source_batch=ba
 e3 = rel(s, s_full[lo:hi])
 yb, (b_lo, b_hi) = D.nfft_adjoint_batch_sharded(x, pos, batch, N, m, batch_size=B, gather_output=True)
 e4 = rel(yb, full)
-errs = torch.tensor([e1, e2, e3, e4], device=dev)
+# B a multiple of the world size: reduce-scatter into whole grids per rank, spectra all-gathered / kept local
+Bw = world
+nw = (n // Bw) * Bw
+batch_w = torch.arange(nw, device=dev) // (nw // Bw)
+full_w = T.nfft_adjoint(x[:nw], pos[:nw], batch_w, N, m, batch_size=Bw)
+lo, hi = D.shard_points(nw, world, rank)
+yw = D.nfft_adjoint_point_sharded(x[lo:hi], pos[lo:hi], batch_w[lo:hi], N, m, batch_size=Bw)
+e5 = rel(yw, full_w)
+ywl, (o_lo, o_hi) = D.nfft_adjoint_point_sharded(x[lo:hi], pos[lo:hi], batch_w[lo:hi], N, m, batch_size=Bw,
+                                                 scatter_output=True)
+e6 = rel(ywl, full_w[o_lo:o_hi])
+errs = torch.tensor([e1, e2, e3, e4, e5, e6], device=dev)
 dist.all_reduce(errs, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("dist check (max over ranks) adjoint_point %.2e forward_point %.2e fastsum_point %.2e adjoint_batch %.2e" % tuple(errs.tolist()))
+    print("dist check (max over ranks) adjoint_point %.2e forward_point %.2e fastsum_point %.2e adjoint_batch %.2e "
+          "adjoint_point_reduce_scatter %.2e (local %.2e)" % tuple(errs.tolist()))
     assert errs.max().item() < 1e-5
 dist.destroy_process_group()

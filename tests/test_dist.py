@@ -86,6 +86,17 @@ def _worker(rank, world, port, results):
                                          cutoff=m, batch_size=B, engine=eng)
         ref = O.nfft_fastsum(x, co, (pos * 0.5).astype(np.float32), None, batch, batch, m=m)
         out["fastsum_point"] = O.rel_l2(s.numpy(), ref[lo:hi])
+        # ---- point sharding with B a multiple of the world size: reduce-scatter into whole grids per rank
+        n2 = 2 * (pos.shape[0] // B)                       # the points of batch entries 0 and 1
+        pos2, batch2, x2 = pos[:n2], batch[:n2], x[:n2]
+        lo2, hi2 = D.shard_points(n2, world, rank)
+        full2 = O.nfft_adjoint(x2, pos2, batch2, N, m)
+        y2 = D.nfft_adjoint_point_sharded(tx[lo2:hi2], tp[lo2:hi2], tb[lo2:hi2], N, m, batch_size=2, engine=eng)
+        out["adj_point_rs"] = O.rel_l2(y2.numpy(), full2)
+        y2l, (o_lo, o_hi) = D.nfft_adjoint_point_sharded(tx[lo2:hi2], tp[lo2:hi2], tb[lo2:hi2], N, m, batch_size=2,
+                                                         engine=eng, scatter_output=True)
+        out["adj_point_rs_local"] = O.rel_l2(y2l.numpy(), full2[o_lo:o_hi])
+        out["owned_rs"] = (o_lo, o_hi)
         # ---- batch sharding: each rank transforms the batch entries it owns
         adj = lambda xx, pp, bb, NN, mm, ro, batch_size: torch.from_numpy(
             O.nfft_adjoint(xx.numpy(), pp.numpy(), bb.numpy(), NN, mm, ro) if pp.shape[0] else
@@ -111,8 +122,10 @@ def test_sharded_transforms_world_size_2():
         res = dict(results)
     assert set(res) == {0, 1}
     for rank, out in res.items():
-        for key in ("adj_point", "fwd_point", "fastsum_point", "adj_batch", "adj_batch_gathered", "fwd_batch"):
+        for key in ("adj_point", "adj_point_rs", "adj_point_rs_local", "fwd_point", "fastsum_point", "adj_batch",
+                    "adj_batch_gathered", "fwd_batch"):
             assert out[key] < 1e-5, (rank, key, out[key])
+    assert res[0]["owned_rs"] == (0, 1) and res[1]["owned_rs"] == (1, 2)
     # ownership: disjoint, contiguous, covering
     assert res[0]["owned"][:2] == (0, 2) and res[1]["owned"][:2] == (2, 3)
     assert res[0]["owned"][3] == res[1]["owned"][2] and res[1]["owned"][3] == 360

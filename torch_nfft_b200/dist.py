@@ -8,9 +8,11 @@ The reference has no multi-device path at all
   contiguous range of batch entries.  No communication.
 * point sharding  -- a single huge point set is split by points.  Spreading is linear in the
   points, so each rank spreads its slice into a *partial* oversampled grid and the partial grids
-  are summed over the ranks (all-reduce: reduce-scatter + all-gather inside NCCL, in-switch with
-  NVLS); the small FFT / spectral stage then runs redundantly on every rank, and each rank
-  gathers at its own target points.  Outputs indexed by points stay sharded.
+  are summed over the ranks.  Adjoint with B a multiple of the world size: ONE NCCL reduce-scatter
+  leaves whole summed grids on each rank, which runs FFT + unpack for its batch entries only.
+  Otherwise (a single grid, fastsum): all-reduce (in-switch with NVLS), the small FFT / spectral
+  stage runs redundantly on every rank, and each rank gathers at its own target points.  Outputs
+  indexed by points stay sharded.
 
 The compute stages are the split entry points of the C ABI (nfftb200_spread / _adjoint_finish /
 _forward_begin / _gather / _fastsum_middle).  They are injected through an `engine` object so the
@@ -143,21 +145,67 @@ def _sum_over_ranks(grid, group):
     return grid
 
 
+def _reduce_scatter_rows(grid, group):
+    """Sum the partial grids over the ranks and leave rank r with rows [r*R, (r+1)*R) of the sum,
+    R = rows / world (whole grids per rank: the FFT stage then needs no further exchange).
+    NCCL: one reduce-scatter over NVLink; gloo (CPU tests) has none, so all-reduce + slice."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rows = grid.shape[0] // world
+    flat = torch.view_as_real(grid) if grid.is_complex() else grid
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((rows,) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
+        dist.reduce_scatter_tensor(out, flat.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        out = flat[rank * rows:(rank + 1) * rows].contiguous()
+    return torch.view_as_complex(out) if grid.is_complex() else out
+
+
+def _all_gather_batches(y_local, group):
+    world = dist.get_world_size(group)
+    flat = torch.view_as_real(y_local) if y_local.is_complex() else y_local
+    out = torch.empty((world * flat.shape[0],) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, flat.contiguous(), group=group)
+    return torch.view_as_complex(out) if y_local.is_complex() else out
+
+
 # --------------------------------------------------------------------------------------
 # point-sharded transforms: every rank passes ITS slice of the points
 # --------------------------------------------------------------------------------------
 def nfft_adjoint_point_sharded(x, pos, batch=None, bandwidth=16, cutoff=3, real_output=False, *, batch_size=None,
-                               group=None, engine=None):
-    """Adjoint NFFT of a point set that is split across ranks.  Returns the full spectrum
-    [B, N..N, *cols] on every rank."""
+                               group=None, engine=None, scatter_output=False):
+    """Adjoint NFFT of a point set that is split across ranks.
+
+    Every rank spreads its points into a partial oversampled grid.  If the number of batch entries is
+    a multiple of the world size the partial grids are summed with ONE reduce-scatter into whole
+    grids per rank, each rank runs FFT + unpack for its B / world entries only,
+    and the (2^d times smaller) spectra are all-gathered unless `scatter_output`; otherwise the grids
+    are all-reduced and the spectral stage runs redundantly.
+
+    Returns the full spectrum [B, N..N, *cols] on every rank, or with scatter_output=True
+    `(y_local, (b_lo, b_hi))`, the spectra of the batch entries this rank owns.
+    """
     eng = engine or _default_engine
     d = pos.shape[1]
     B = int(batch_size) if batch_size is not None else (1 if batch is None else None)
     if B is None:
         raise RuntimeError("point-sharded transforms with a batch vector need batch_size= (the global value)")
+    cols = tuple(x.shape[1:])
     grid = eng.spread(x, pos, batch, B, bandwidth, cutoff)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1 and B % world == 0:
+        rank = dist.get_rank(group)
+        grid = _reduce_scatter_rows(grid, group)
+        y_local = eng.adjoint_finish(grid, d, B // world, cols, bandwidth, cutoff, real_output)
+        if scatter_output:
+            return y_local, (rank * (B // world), (rank + 1) * (B // world))
+        return _all_gather_batches(y_local, group)
     grid = _sum_over_ranks(grid, group)
-    return eng.adjoint_finish(grid, d, B, tuple(x.shape[1:]), bandwidth, cutoff, real_output)
+    y = eng.adjoint_finish(grid, d, B, cols, bandwidth, cutoff, real_output)
+    if scatter_output:
+        lo, hi = split_range(B, world, dist.get_rank(group) if world > 1 else 0)
+        return y[lo:hi], (lo, hi)
+    return y
 
 
 def nfft_forward_point_sharded(xhat, pos, batch=None, cutoff=3, real_output=False, *, batch_size=None, group=None,
