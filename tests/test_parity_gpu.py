@@ -227,6 +227,20 @@ def test_all_points_in_one_cell():
     assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(y.cpu().numpy(), pos, None, 3)) < TOL
 
 
+def test_clustered_points_split_heavy_columns():
+    """A tight Gaussian cluster: a few supercell columns of the 3D register-stencil sweep hold most of a
+    tile's points, so they are split into z-range work units (window_reg.cuh make_units)."""
+    rng = np.random.default_rng(16)
+    n, N, m = 30000, 32, 4
+    pos = (np.array([0.11, -0.2, 0.31]) + 0.03 * rng.standard_normal((n, 3))).astype(np.float32)
+    pos = (((pos + 0.5) % 1.0) - 0.5).astype(np.float32)
+    x = make_values(rng, (n, 1), False)
+    y = T.nfft_adjoint(cuda(x), cuda(pos), None, N, m)
+    assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(x, pos, None, N, m)) < TOL
+    f = T.nfft_forward(y, cuda(pos), None, m, real_output=True)
+    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(y.cpu().numpy(), pos, None, m, real_output=True)) < TOL
+
+
 def test_non_contiguous_inputs_and_side_stream():
     rng = np.random.default_rng(7)
     pos = rng.random((500, 2), dtype=np.float32) - 0.5

@@ -240,7 +240,7 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
 __device__ __forceinline__ void make_units(const int* s_start, int ncols, int nsz, int* s_units, int* s_nunits) {
     __shared__ int s_raw[64], s_rawcnt[64];
     const int total = s_start[ncols * nsz] - s_start[0];
-    const int maxseg = NFFT_REG_SPLIT ? (64 / ncols < 4 ? 64 / ncols : 4) : 1;
+    const int maxseg = NFFT_REG_SPLIT && ncols <= 32 ? (64 / ncols < 4 ? 64 / ncols : 4) : 1;  // ncols <= 64
     if ((int)threadIdx.x < ncols) {
         const int c0 = threadIdx.x * nsz;
         const int lo = s_start[c0], cnt = s_start[c0 + nsz] - lo;
