@@ -10,6 +10,10 @@ CONFIGS = {
     "c4": (3, 128, 4, 2 ** 24, 4, 1),
     "c5gpu": (3, 64, 4, 2 ** 23, 1, 1),
     "c4small": (3, 128, 4, 2 ** 20, 4, 1),
+    "c4m3": (3, 128, 3, 2 ** 24, 4, 1),   # the reference's default cutoff
+    "c4m2": (3, 128, 2, 2 ** 24, 4, 1),
+    "c3m3": (2, 256, 3, 2 ** 23, 16, 8),
+    "c4m6": (3, 128, 6, 2 ** 22, 4, 1),   # m > 4: team kernels
 }
 
 

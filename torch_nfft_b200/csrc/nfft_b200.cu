@@ -11,6 +11,7 @@
 #include "window.cuh"
 #include "window_reg.cuh"
 #include "window_reg2d.cuh"
+#include "window1d.cuh"
 #include <stdlib.h>
 
 #include <initializer_list>
@@ -167,6 +168,8 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     if (g.use_reg) ncomp = 1;
     // 2D register-stencil kernels: m = 3 or 4, up to 8 float components per pass
     if (d == 2 && (m == 3 || m == 4) && !no_reg) g.use_reg = 2;
+    // 1D: cell-owner spread / point-owner gather (window1d.cuh), any m, real and complex
+    if (d == 1 && !no_reg) g.use_reg = 3;
     g.ncomp = ncomp;
     int T[3] = {1, 1, 1};
     if (d == 1) {
@@ -207,6 +210,10 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     g.pmax = (int)(pm < 256 ? 256 : (pm > 2048 ? 2048 : pm));
     if (g.use_reg == 1) g.pmax = kRegMaxPts;
     if (g.use_reg == 2) g.pmax = kReg2MaxPts;
+    if (g.use_reg == 3) {
+        pm = n_points / (148 * 4);
+        g.pmax = (int)(pm < 512 ? 512 : (pm > kW1MaxPts ? kW1MaxPts : pm));
+    }
     int threads = (team + 31) / 32 * 32;
     g.spread_threads = threads < 64 ? 64 : threads;
     return NFFTB200_OK;
@@ -282,6 +289,29 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
             if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
             NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             NF_LAUNCH(kern, (unsigned)sp.max_items, kReg2Threads, smem, st, g, a);
+        }
+        return NFFTB200_OK;
+    }
+    if (g.use_reg == 3) {
+        const bool pow2 = (g.M & (g.M - 1)) == 0;
+        int ncomp = g.ncomp;
+        for (int k0 = 0; k0 < g.K; k0 += ncomp) {
+            ncomp = g.ncomp;
+            while (ncomp > g.K - k0) ncomp >>= 1;
+            if (g.cplx && ncomp < 2) ncomp = 2;
+            a.k0 = k0;
+            WindowKernel kern = nullptr;
+#define NF_W1_CASE(C_)                                                                                     \
+            if (ncomp == C_)                                                                               \
+                kern = spread ? (pow2 ? spread1d_kernel<C_, true> : spread1d_kernel<C_, false>)            \
+                              : (pow2 ? gather1d_kernel<C_, true> : gather1d_kernel<C_, false>);
+            NF_W1_CASE(1) NF_W1_CASE(2) NF_W1_CASE(4) NF_W1_CASE(8)
+#undef NF_W1_CASE
+            if (!kern) NF_FAIL(NFFTB200_ERR_INVALID, "no 1D kernel for ncomp=%d", ncomp);
+            const size_t smem = spread ? w1_spread_smem_bytes(g, ncomp) : w1_gather_smem_bytes(g, ncomp);
+            if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
+            NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NF_LAUNCH(kern, (unsigned)sp.max_items, kW1Threads, smem, st, g, a);
         }
         return NFFTB200_OK;
     }

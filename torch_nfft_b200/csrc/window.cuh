@@ -197,6 +197,78 @@ __device__ __forceinline__ void for_each_quad(const Geom& g, const TileCtx& t, F
     }
 }
 
+// Adds the CTA's padded tile (NCOMP component planes in shared memory) into the global grid.
+template <int DIM, int NCOMP>
+__device__ __forceinline__ void flush_tile(const Geom& g, const TileCtx& t, const WindowArgs& a, const float* tile) {
+    // vector reductions into the global grid; untouched (== 0) quads are skipped
+    if (!g.cplx) {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) {
+                if (a.k0 + k < g.K) {
+                    const float* s = tile + (size_t)k * g.tile_elems + so;
+                    const float4 val = make_float4(s[0], s[1], s[2], s[3]);
+                    if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) {
+                        float4* dst = reinterpret_cast<float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell);
+                        atomicAdd(dst, val);
+                    }
+                }
+            }
+        });
+    } else {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k + 1 < NCOMP; k += 2) {
+                if (a.k0 + k < g.K) {
+                    const float* re = tile + (size_t)k * g.tile_elems + so;
+                    const float* im = tile + (size_t)(k + 1) * g.tile_elems + so;
+                    float* dst = a.grid + grid_plane(g, t.b, a.k0 + k) + 2 * cell;
+                    const float4 v0 = make_float4(re[0], im[0], re[1], im[1]);
+                    const float4 v1 = make_float4(re[2], im[2], re[3], im[3]);
+                    if (v0.x != 0.f || v0.y != 0.f || v0.z != 0.f || v0.w != 0.f)
+                        atomicAdd(reinterpret_cast<float4*>(dst), v0);
+                    if (v1.x != 0.f || v1.y != 0.f || v1.z != 0.f || v1.w != 0.f)
+                        atomicAdd(reinterpret_cast<float4*>(dst + 4), v1);
+                }
+            }
+        });
+    }
+}
+
+// Stages the CTA's padded tile from the global grid into shared memory.
+template <int DIM, int NCOMP>
+__device__ __forceinline__ void load_tile(const Geom& g, const TileCtx& t, const WindowArgs& a, float* tile) {
+    // periodic wrap resolved per quad
+    if (!g.cplx) {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) {
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.k0 + k < g.K)
+                    val = __ldg(reinterpret_cast<const float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell));
+                float* s = tile + (size_t)k * g.tile_elems + so;
+                s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
+            }
+        });
+    } else {
+        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
+#pragma unroll
+            for (int k = 0; k < NCOMP; k += 2) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (a.k0 + k < g.K) {
+                    const float* src = a.grid + grid_plane(g, t.b, a.k0 + k) + 2 * cell;
+                    v0 = __ldg(reinterpret_cast<const float4*>(src));
+                    v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                }
+                float* re = tile + (size_t)k * g.tile_elems + so;
+                float* im = tile + (size_t)(k + 1 < NCOMP ? k + 1 : k) * g.tile_elems + so;
+                re[0] = v0.x; re[1] = v0.z; re[2] = v1.x; re[3] = v1.z;
+                if (k + 1 < NCOMP) { im[0] = v0.y; im[1] = v0.w; im[2] = v1.y; im[3] = v1.w; }
+            }
+        });
+    }
+}
+
 // ======================================================================================
 // adjoint spreading
 // ======================================================================================
@@ -339,39 +411,7 @@ spread_kernel(const Geom g, const WindowArgs a) {
         __syncthreads();
     }
 
-    // flush: vector reductions into the global grid; untouched (== 0) quads are skipped
-    if (!g.cplx) {
-        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
-#pragma unroll
-            for (int k = 0; k < NCOMP; ++k) {
-                if (a.k0 + k < g.K) {
-                    const float* s = tile + (size_t)k * g.tile_elems + so;
-                    const float4 val = make_float4(s[0], s[1], s[2], s[3]);
-                    if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) {
-                        float4* dst = reinterpret_cast<float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell);
-                        atomicAdd(dst, val);
-                    }
-                }
-            }
-        });
-    } else {
-        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
-#pragma unroll
-            for (int k = 0; k + 1 < NCOMP; k += 2) {
-                if (a.k0 + k < g.K) {
-                    const float* re = tile + (size_t)k * g.tile_elems + so;
-                    const float* im = tile + (size_t)(k + 1) * g.tile_elems + so;
-                    float* dst = a.grid + grid_plane(g, t.b, a.k0 + k) + 2 * cell;
-                    const float4 v0 = make_float4(re[0], im[0], re[1], im[1]);
-                    const float4 v1 = make_float4(re[2], im[2], re[3], im[3]);
-                    if (v0.x != 0.f || v0.y != 0.f || v0.z != 0.f || v0.w != 0.f)
-                        atomicAdd(reinterpret_cast<float4*>(dst), v0);
-                    if (v1.x != 0.f || v1.y != 0.f || v1.z != 0.f || v1.w != 0.f)
-                        atomicAdd(reinterpret_cast<float4*>(dst + 4), v1);
-                }
-            }
-        });
-    }
+    flush_tile<DIM, NCOMP>(g, t, a, tile);
 }
 
 // ======================================================================================
@@ -400,35 +440,7 @@ gather_kernel(const Geom g, const WindowArgs a) {
         stage_prefetch<DIM>(regs, a, t.p_lo, (int)(left < kSubBatch ? left : kSubBatch));
     }
 
-    // stage the padded tile (periodic wrap resolved per quad)
-    if (!g.cplx) {
-        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
-#pragma unroll
-            for (int k = 0; k < NCOMP; ++k) {
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.k0 + k < g.K)
-                    val = __ldg(reinterpret_cast<const float4*>(a.grid + grid_plane(g, t.b, a.k0 + k) + cell));
-                float* s = tile + (size_t)k * g.tile_elems + so;
-                s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
-            }
-        });
-    } else {
-        for_each_quad<DIM>(g, t, [&](int so, long long cell) {
-#pragma unroll
-            for (int k = 0; k < NCOMP; k += 2) {
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (a.k0 + k < g.K) {
-                    const float* src = a.grid + grid_plane(g, t.b, a.k0 + k) + 2 * cell;
-                    v0 = __ldg(reinterpret_cast<const float4*>(src));
-                    v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                }
-                float* re = tile + (size_t)k * g.tile_elems + so;
-                float* im = tile + (size_t)(k + 1 < NCOMP ? k + 1 : k) * g.tile_elems + so;
-                re[0] = v0.x; re[1] = v0.z; re[2] = v1.x; re[3] = v1.z;
-                if (k + 1 < NCOMP) { im[0] = v0.y; im[1] = v0.w; im[2] = v1.y; im[3] = v1.w; }
-            }
-        });
-    }
+    load_tile<DIM, NCOMP>(g, t, a, tile);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
