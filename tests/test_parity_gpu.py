@@ -385,7 +385,7 @@ def test_sort_reuse_between_adjoint_and_forward():
     first = _lib.launch_count() - before
     f = T.nfft_forward(y, tp, tb, 4, real_output=True)  # same points, same tiling: no second sort
     second = _lib.launch_count() - before - first
-    assert second < first - 8, (first, second)
+    assert second <= 4 and first - second >= 5, (first, second)  # the binning alone is >= 5 launches
     ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
     assert O.rel_l2(y.cpu().numpy(), ref_y) < TOL
     assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, 4, real_output=True)) < TOL

@@ -311,7 +311,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
             const size_t smem = spread ? w1_spread_smem_bytes(g, ncomp) : w1_gather_smem_bytes(g, ncomp);
             if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
             NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            NF_LAUNCH(kern, (unsigned)sp.max_items, kW1Threads, smem, st, g, a);
+            NF_LAUNCH(kern, (unsigned)sp.max_items, spread ? kW1SpreadThreads : kW1Threads, smem, st, g, a);
         }
         return NFFTB200_OK;
     }

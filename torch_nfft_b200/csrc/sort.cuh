@@ -103,6 +103,26 @@ scan_final_kernel(const uint32_t* in, uint32_t* out, long long count, const uint
     if (blockIdx.x == 0 && threadIdx.x == 0) out[count] = partial[nparts];
 }
 
+// Small arrays (bin counts, chunk counts, the digit tables of small sorts): one block, one launch
+// instead of three.  Every thread owns a contiguous run of `per` items; in may alias out.
+constexpr long long kScanSmallMax = 1024 * 8;  // (a 64K-entry digit table through one block costs 85 us)
+__global__ void __launch_bounds__(1024)
+scan_small_kernel(const uint32_t* in, uint32_t* out, int count, int per) {
+    __shared__ uint32_t s_warp[33];
+    const int lo = threadIdx.x * per;
+    const int hi = lo + per < count ? lo + per : count;
+    uint32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += in[i];
+    uint32_t total;
+    uint32_t ex = block_excl_scan(s, s_warp, &total);
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t v = in[i];
+        out[i] = ex;
+        ex += v;
+    }
+    if (threadIdx.x == 0) out[count] = total;
+}
+
 inline size_t scan_scratch_bytes(long long count) {
     long long nparts = (count + kScanTile - 1) / kScanTile;
     if (nparts < 1) nparts = 1;
@@ -112,6 +132,11 @@ inline size_t scan_scratch_bytes(long long count) {
 // exclusive scan of `count` uint32 (count >= 0); writes count+1 entries to out.
 inline int scan_exclusive(const uint32_t* in, uint32_t* out, long long count, uint32_t* scratch,
                           cudaStream_t st) {
+    if (count <= kScanSmallMax) {
+        const int per = (int)((count + 1023) / 1024);
+        NF_LAUNCH(scan_small_kernel, 1, 1024, 0, st, in, out, (int)count, per < 1 ? 1 : per);
+        return NFFTB200_OK;
+    }
     int nparts = (int)((count + kScanTile - 1) / kScanTile);
     if (nparts < 1) nparts = 1;
     NF_LAUNCH(scan_reduce_kernel, nparts, kScanThreads, 0, st, in, count, scratch);

@@ -18,13 +18,14 @@
 
 namespace nfftb200 {
 
-constexpr int kW1Threads = 256;
-constexpr int kW1MaxPts = 2048;  // points per work item (chunk)
+constexpr int kW1Threads = 256;        // gather
+constexpr int kW1SpreadThreads = 288;  // 9 warps: the 512 + 20 padded cells of a tile take 2 rounds, not 3
+constexpr int kW1MaxPts = 2048;        // points per work item (chunk)
 
 inline size_t w1_spread_smem_bytes(const Geom& g, int ncomp) {
-    // tile | point positions | values | cell start[T+1], cursor[T]
+    // tile | point positions | values | cell start[T+1], cursor[T] | cell of each point (u16)
     return (size_t)ncomp * g.tile_elems * 4 + (size_t)kW1MaxPts * 4 + (size_t)kW1MaxPts * ncomp * 4 +
-           (size_t)(2 * g.T[0] + 4) * 4;
+           (size_t)(2 * g.T[0] + 4) * 4 + (size_t)kW1MaxPts * 2;
 }
 inline size_t w1_gather_smem_bytes(const Geom& g, int ncomp) { return (size_t)ncomp * g.tile_elems * 4; }
 
@@ -41,7 +42,7 @@ __device__ __forceinline__ float tap_1d(const Geom& g, float p, float pm, float 
 }
 
 template <int NCOMP, bool POW2>
-__global__ void __launch_bounds__(kW1Threads)
+__global__ void __launch_bounds__(kW1SpreadThreads)
 spread1d_kernel(const Geom g, const WindowArgs a) {
     extern __shared__ __align__(16) float smem[];
     TileCtx t;
@@ -52,12 +53,13 @@ spread1d_kernel(const Geom g, const WindowArgs a) {
     float* s_x = s_p + kW1MaxPts;
     int* s_start = reinterpret_cast<int*>(s_x + (size_t)kW1MaxPts * NCOMP);
     int* s_cur = s_start + T + 2;
+    unsigned short* s_c = reinterpret_cast<unsigned short*>(s_cur + T + 2);
 
-    for (int i = threadIdx.x; i < T; i += kW1Threads) s_cur[i] = 0;
+    for (int i = threadIdx.x; i < T; i += kW1SpreadThreads) s_cur[i] = 0;
     __syncthreads();
 
     // bucket the chunk's points by cell of the tile
-    constexpr int kPer = kW1MaxPts / kW1Threads;
+    constexpr int kPer = (kW1MaxPts + kW1SpreadThreads - 1) / kW1SpreadThreads;
     const int cnt = (int)(t.p_hi - t.p_lo);
     const int lo0 = t.org[0] + g.org[0];  // first cell of the tile
     const float Mf = (float)g.M;
@@ -66,7 +68,7 @@ spread1d_kernel(const Geom g, const WindowArgs a) {
     int cell[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-        const int e = threadIdx.x + k * kW1Threads;
+        const int e = threadIdx.x + k * kW1SpreadThreads;
         cell[k] = -1;
         if (e < cnt) {
             src[k] = a.perm[t.p_lo + e];
@@ -96,13 +98,15 @@ spread1d_kernel(const Geom g, const WindowArgs a) {
         if (threadIdx.x == 0) s_start[T] = running;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < T; i += kW1Threads) s_cur[i] = s_start[i];
+    for (int i = threadIdx.x; i < T; i += kW1SpreadThreads) s_cur[i] = s_start[i];
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         if (cell[k] >= 0) {
             const int dst = atomicAdd(&s_cur[cell[k]], 1);
-            s_p[dst] = pt[k];
+            const float pm = pt[k] * Mf;
+            s_p[dst] = POW2 ? pm - floorf(pm) : pt[k];  // exact fraction when M is a power of two
+            s_c[dst] = (unsigned short)cell[k];
 #pragma unroll
             for (int c = 0; c < NCOMP; ++c)
                 s_x[dst * NCOMP + c] = a.k0 + c < g.K ? a.xin[(size_t)src[k] * g.K + a.k0 + c] : 0.f;
@@ -112,23 +116,29 @@ spread1d_kernel(const Geom g, const WindowArgs a) {
 
     // one thread per padded cell j: taps of core cells c with l = j - (c + org - m) in [0, L)
     const int shift = g.org[0] - g.m;
-    for (int j = threadIdx.x; j < g.tile_elems; j += kW1Threads) {
+    for (int j = threadIdx.x; j < g.tile_elems; j += kW1SpreadThreads) {
         float acc[NCOMP];
 #pragma unroll
         for (int c = 0; c < NCOMP; ++c) acc[c] = 0.f;
         int c_hi = j - shift, c_lo = c_hi - (g.L - 1);
         c_lo = c_lo < 0 ? 0 : c_lo;
         c_hi = c_hi > T - 1 ? T - 1 : c_hi;
-        if (c_lo <= c_hi) {
-            int c = c_lo, c_end = s_start[c_lo + 1];
-            for (int q = s_start[c_lo]; q < s_start[c_hi + 1]; ++q) {
-                while (q >= c_end) c_end = s_start[++c + 1];
+        // one flat loop over the points of cells c_lo .. c_hi (contiguous after the bucketing): nested
+        // per-cell loops diverge badly, the lanes of a warp own cells with different point counts
+        const int q_end = c_lo <= c_hi ? s_start[c_hi + 1] : 0;
+        for (int q = c_lo <= c_hi ? s_start[c_lo] : 0; q < q_end; ++q) {
+            const int l = j - shift - (int)s_c[q];  // tap of point q that lands on cell j
+            float w;
+            if (POW2) {
+                const float tt = s_p[q] + (float)(g.m - l);  // s_p holds the exact fraction: one rounding
+                w = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;
+            } else {
                 const float p = s_p[q];
                 const float pm = p * Mf;
-                const float w = tap_1d<POW2>(g, p, pm, floorf(pm), j - shift - c);
-#pragma unroll
-                for (int k = 0; k < NCOMP; ++k) acc[k] = fmaf(s_x[q * NCOMP + k], w, acc[k]);
+                w = tap_1d<false>(g, p, pm, floorf(pm), l);
             }
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) acc[k] = fmaf(s_x[q * NCOMP + k], w, acc[k]);
         }
 #pragma unroll
         for (int k = 0; k < NCOMP; ++k) tile[(size_t)k * g.tile_elems + j] = acc[k];
