@@ -10,6 +10,10 @@
 #pragma once
 #include "window_reg.cuh"
 
+#ifndef NFFT_REG2_BANDED
+#define NFFT_REG2_BANDED 1
+#endif
+
 namespace nfftb200 {
 
 constexpr int kReg2Threads = 256;
@@ -231,15 +235,41 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
             }
             __syncwarp();
         }
-        // add the block into the shared tile planes; rows [4 scy, 4 scy + W) live in bands scy .. scy + (W-1)/4
+        // add the block into the shared tile planes, one band of kReg2S tile rows at a time: rows
+        // [4 scy, 4 scy + W) live in bands scy .. scy + (W-1)/4, each guarded by its own lock, so warps
+        // working on overlapping supercells pipeline through the bands instead of excluding each other
+        // for the whole block
         constexpr int kBands = (W + kReg2S - 1) / kReg2S;
+        float* bbase = tile + (scy * kReg2S) * g.sY + scx * kReg2S + padx;
+#if NFFT_REG2_BANDED
+#pragma unroll
+        for (int b = 0; b < kBands; ++b) {
+            if (lane == 0) {
+                while (atomicCAS(&s_lock[scy + b], 0, 1) != 0) __nanosleep(32);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int row = (lane + 32 * q) / W;
+                if (lane + 32 * q < Cfg::COLS && row / kReg2S == b) {
+                    float cur[NCOMP];
+#pragma unroll
+                    for (int c = 0; c < NCOMP; ++c) cur[c] = bbase[(size_t)c * g.tile_elems + coff[q]];
+#pragma unroll
+                    for (int c = 0; c < NCOMP; ++c) bbase[(size_t)c * g.tile_elems + coff[q]] = cur[c] + acc[q][c];
+                }
+            }
+            release_fence();
+            __syncwarp();
+            if (lane == 0) atomicExch(&s_lock[scy + b], 0);
+        }
+#else
         if (lane == 0) {
 #pragma unroll
             for (int b = 0; b < kBands; ++b)
                 while (atomicCAS(&s_lock[scy + b], 0, 1) != 0) __nanosleep(32);  // ascending order: no deadlock
         }
         __syncwarp();
-        float* bbase = tile + (scy * kReg2S) * g.sY + scx * kReg2S + padx;
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             if (lane + 32 * q < Cfg::COLS) {
@@ -256,6 +286,7 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
             for (int b = 0; b < kBands; ++b) atomicExch(&s_lock[scy + b], 0);
         }
+#endif
     }
     __syncthreads();
 
