@@ -10,6 +10,9 @@
 #pragma once
 #include "window_reg.cuh"
 
+#ifndef NFFT_REG2_FFMA2
+#define NFFT_REG2_FFMA2 1
+#endif
 #ifndef NFFT_REG2_BANDED
 #define NFFT_REG2_BANDED 1
 #endif
@@ -203,11 +206,13 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
         if (lo == hi) break;  // supercells are ordered by size: the rest is empty
         const int scx = sc % nsx, scy = sc / nsx;
 
-        float acc[CPL][NCOMP];
+        // channel pairs share one packed fp32x2 FMA (scalar-broadcast weight)
+        constexpr int NC2 = (NCOMP + 1) / 2;
+        float2 acc2[CPL][NC2];
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
-            for (int c = 0; c < NCOMP; ++c) acc[q][c] = 0.f;
+            for (int c = 0; c < NC2; ++c) acc2[q][c] = make_float2(0.f, 0.f);
 
         for (int base = lo; base < hi; base += kReg2Group) {
             const int npts = hi - base < kReg2Group ? hi - base : kReg2Group;
@@ -226,11 +231,22 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
                     for (int c = 0; c < NCOMP; ++c) xs[c] = rec[c];
                 }
+                float2 xs2[NC2];
+#pragma unroll
+                for (int c = 0; c < NC2; ++c) xs2[c] = make_float2(xs[2 * c], 2 * c + 1 < NCOMP ? xs[2 * c + 1] : 0.f);
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
                     const float v = wv[wj[q]] * wv[wi[q]];  // psi(dim 0 = Y) * psi(dim 1 = X)
+                    const float2 vv = make_float2(v, v);
 #pragma unroll
-                    for (int c = 0; c < NCOMP; ++c) acc[q][c] = fmaf(v, xs[c], acc[q][c]);
+                    for (int c = 0; c < NC2; ++c) {
+                        if (NCOMP >= 2 && NFFT_REG2_FFMA2) {
+                            acc2[q][c] = __ffma2_rn(vv, xs2[c], acc2[q][c]);
+                        } else {
+                            acc2[q][c].x = fmaf(v, xs2[c].x, acc2[q][c].x);
+                            acc2[q][c].y = fmaf(v, xs2[c].y, acc2[q][c].y);
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -256,7 +272,7 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
                     for (int c = 0; c < NCOMP; ++c) cur[c] = bbase[(size_t)c * g.tile_elems + coff[q]];
 #pragma unroll
-                    for (int c = 0; c < NCOMP; ++c) bbase[(size_t)c * g.tile_elems + coff[q]] = cur[c] + acc[q][c];
+                    for (int c = 0; c < NCOMP; ++c) bbase[(size_t)c * g.tile_elems + coff[q]] = cur[c] + ((c & 1) ? acc2[q][c >> 1].y : acc2[q][c >> 1].x);
                 }
             }
             release_fence();
@@ -277,7 +293,7 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
                 for (int c = 0; c < NCOMP; ++c) cur[c] = bbase[(size_t)c * g.tile_elems + coff[q]];
 #pragma unroll
-                for (int c = 0; c < NCOMP; ++c) bbase[(size_t)c * g.tile_elems + coff[q]] = cur[c] + acc[q][c];
+                for (int c = 0; c < NCOMP; ++c) bbase[(size_t)c * g.tile_elems + coff[q]] = cur[c] + ((c & 1) ? acc2[q][c >> 1].y : acc2[q][c >> 1].x);
             }
         }
         release_fence();
@@ -380,15 +396,28 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
             stage_windows_2d<Cfg, LC, PITCH, POS>(g, s_rec, s_off, base, npts, win, lane, pow2);
             const float* wv = win;
             for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP) {
-                float part[NCOMP];
+                constexpr int NC2 = (NCOMP + 1) / 2;
+                float2 part2[NC2];
 #pragma unroll
-                for (int c = 0; c < NCOMP; ++c) part[c] = 0.f;
+                for (int c = 0; c < NC2; ++c) part2[c] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
                     const float v = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X); zero for unused positions
+                    const float2 vv = make_float2(v, v);
 #pragma unroll
-                    for (int c = 0; c < NCOMP; ++c) part[c] = fmaf(v, blk[q][c], part[c]);
+                    for (int c = 0; c < NC2; ++c) {
+                        const float2 b2 = make_float2(blk[q][2 * c], 2 * c + 1 < NCOMP ? blk[q][2 * c + 1] : 0.f);
+                        if (NCOMP >= 2 && NFFT_REG2_FFMA2) {
+                            part2[c] = __ffma2_rn(vv, b2, part2[c]);
+                        } else {
+                            part2[c].x = fmaf(v, b2.x, part2[c].x);
+                            part2[c].y = fmaf(v, b2.y, part2[c].y);
+                        }
+                    }
                 }
+                float part[NCOMP];
+#pragma unroll
+                for (int c = 0; c < NCOMP; ++c) part[c] = (c & 1) ? part2[c >> 1].y : part2[c >> 1].x;
                 warp_reduce_channels<NCOMP>(part, lane);
                 if ((lane & (kLanesPerChannel - 1)) == 0) {
                     const int c = lane / kLanesPerChannel;
