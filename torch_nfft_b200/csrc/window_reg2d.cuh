@@ -135,14 +135,14 @@ __device__ __forceinline__ void stage_windows_2d(const Geom& g, const float* s_r
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
-                dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
+                dst[l] = window_exp(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
         } else {
             const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = (float)(bd - (double)l);
-                dst[l] = expf(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;
+                dst[l] = window_exp(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;
             }
         }
     }
