@@ -41,8 +41,15 @@ static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather re
 #ifndef NFFT_REG_GATHER_ORDER
 #define NFFT_REG_GATHER_ORDER 1
 #endif
+#ifndef NFFT_REG_GSLOTS
+#define NFFT_REG_GSLOTS 8
+#endif
+constexpr int kGatherSlots = NFFT_REG_GSLOTS;  // unrolled point slots of the gather (a power of two <= kRegGroup)
+#ifndef NFFT_REG_SLOTTED
+#define NFFT_REG_SLOTTED 1
+#endif
 #ifndef NFFT_REG_PTUNROLL
-#define NFFT_REG_PTUNROLL 1
+#define NFFT_REG_PTUNROLL 2
 #endif
 constexpr int kPtUnroll = NFFT_REG_PTUNROLL;  // unroll factor of the spread point loop
 
@@ -487,6 +494,50 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                 stage_windows<Cfg, LC, NFFT_REG_SCALEZ>(g, s_pts, s_off, base, npts, win, lane, pow2);
                 const float* wv = win;          // x / y windows of the point
                 const float* wzp = win + kXY;   // z window of the point
+#if NFFT_REG_SLOTTED
+                // One copy of the point body per slot of the round (window loads with immediate offsets),
+                // entered through a switch; a slot that ends a supercell leaves the switch so that the ONE
+                // copy of the add-out code above it runs, and the switch is re-entered at the next slot.
+                auto point = [&](const float* wv, const float* wzp) {
+                    float2 wz[ZP];
+#pragma unroll
+                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                        const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
+                        wz[2 * l4] = make_float2(w4.x, w4.y);
+                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
+                    }
+                    float v[CPL];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) v[q] = wv[wj[q]] * wv[wi[q]];  // x value folded into wz
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const float2 vv = make_float2(v[q], v[q]);
+#pragma unroll
+                        for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
+                    }
+                    asm volatile("" ::: "memory");  // keeps the next slot's loads from being hoisted
+                };
+                static_assert(!NFFT_REG_SLOTTED || (NFFT_REG_SCALEZ && kRegGroup == 8), "slotted sweep: 8 slots, value in wz");
+                for (int gp = 0; gp < npts;) {
+                    while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
+                        advance(scz, false);
+                        ++scz;
+                        next_end = s_start[c0 + scz + 1];
+                    }
+                    const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
+#define NFFT_SLOT(K)                                                                       \
+                    case K:                                                                \
+                        point(win + K * 2 * Cfg::XYP, win + kXY + K * Cfg::ZWP);           \
+                        gp = K + 1;                                                        \
+                        if (K + 1 >= stop) break;
+                    switch (gp) {
+                        NFFT_SLOT(0) NFFT_SLOT(1) NFFT_SLOT(2) NFFT_SLOT(3)
+                        NFFT_SLOT(4) NFFT_SLOT(5) NFFT_SLOT(6) NFFT_SLOT(7)
+                        default: break;
+                    }
+#undef NFFT_SLOT
+                }
+#else
 #pragma unroll kPtUnroll
                 for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
                     while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
@@ -517,7 +568,15 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
                         for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
                     }
+#if NFFT_REG_PTUNROLL > 1
+                    // unrolled point loop: half of the window loads get immediate offsets; the barrier keeps
+                    // the compiler from hoisting the next point's loads (register pressure).  Measured at
+                    // c4: 4.36 ms rolled, 4.28 ms by 2; by 4 or 8 the copies of the add-out code thrash
+                    // the instruction cache (6.1 / 9.6 ms).
+                    asm volatile("" ::: "memory");
+#endif
                 }
+#endif
                 __syncwarp();
             }
             // the unit's last point lies in supercell scz: everything the block holds goes out
@@ -655,13 +714,19 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
             stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
-            float part[kRegGroup];
-#pragma unroll
-            for (int gp = 0; gp < kRegGroup; ++gp) part[gp] = 0.f;
             const float* wv = win;
             const float* wzp = win + kXY;
+            // the round is evaluated in sub-rounds of kGatherSlots unrolled point slots (static registers
+            // for the partial sums): 8 slots in one go make the hot loop larger than the instruction cache
+            // likes (every slot carries a copy of the block slide)
+#pragma unroll 1
+            for (int g0 = 0; g0 < npts; g0 += kGatherSlots) {
+            float part[kGatherSlots];
 #pragma unroll
-            for (int gp = 0; gp < kRegGroup; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
+            for (int sl = 0; sl < kGatherSlots; ++sl) part[sl] = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < kGatherSlots; ++sl, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
+                const int gp = g0 + sl;
                 if (gp < npts) {
                     while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
                         ++scz;
@@ -702,17 +767,18 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                         sum = ffma2(make_float2(w, w), inner, sum);
                     }
 #endif
-                    part[gp] = sum.x + sum.y;
+                    part[sl] = sum.x + sum.y;
                 }
             }
-            // sum the kRegGroup partials over the warp (transpose reduction: 9 shuffles for 8 values);
-            // lane 4 p then holds the value of point p of the round
-            warp_reduce_channels<kRegGroup>(part, lane);
-            constexpr int kLanesPerPoint = 32 / kRegGroup;
-            if ((lane & (kLanesPerPoint - 1)) == 0 && lane / kLanesPerPoint < npts) {
-                const int gp = lane / kLanesPerPoint;
+            // sum the partials over the warp (transpose reduction: 9 shuffles for 8 values, 7 for 4);
+            // lane (32 / kGatherSlots) p then holds the value of point g0 + p
+            warp_reduce_channels<kGatherSlots>(part, lane);
+            constexpr int kLanesPerPoint = 32 / kGatherSlots;
+            if ((lane & (kLanesPerPoint - 1)) == 0 && g0 + lane / kLanesPerPoint < npts) {
+                const int gp = g0 + lane / kLanesPerPoint;
                 const uint32_t i = (uint32_t)__float_as_int(s_pts[base + gp].w);
                 a.yout[(size_t)i * g.K + a.k0] = part[0];
+            }
             }
             __syncwarp();
         }
