@@ -328,6 +328,28 @@ def run_ours(args):
     _lib.profile_enable(False)
     clocks = sampler.stop(t0, t1) if sampler else None
 
+    graph_info = None
+    if args.cuda_graph:
+        # the same step captured once into a CUDA graph and replayed (no per-launch host cost: matters for
+        # the launch-bound 1D workload c2, 28 launches per pair); reported next to the eager numbers
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(compute_stream)
+        with torch.cuda.stream(side):
+            step_device()
+        compute_stream.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            step_device()
+        captured = _lib.launch_count() - l0
+        for _ in range(3):
+            graph.replay()
+        ms_graph, _, _ = timed(graph.replay, args.steps)
+        graph_info = {"ms_per_step": ms_graph / args.steps, "value": n * world / (ms_graph / args.steps * 1e-3),
+                      "unit": "points/s", "kernels_per_replay": int(captured)}
+        del graph
+
     if args.no_extras:
         ms_e2e = float("nan")
     else:
@@ -388,6 +410,8 @@ def run_ours(args):
             "stage_ms_per_step": stage_ms,
             "cpu_baseline": cpu_baseline_ndft(args.workload) if (world == 1 and not args.no_extras) else None,
         }
+        if graph_info is not None:
+            out["cuda_graph"] = graph_info
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -475,6 +499,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="also time the step captured into a CUDA graph (adds a `cuda_graph` object to the line)")
     ap.add_argument("--no-extras", action="store_true", help="development: skip the e2e and cpu_baseline legs")
     ap.add_argument("--ref-points", type=int, default=0,
                     help="points per step of the reference CUDA arm (bounded sample of the workload); 0 = as many "

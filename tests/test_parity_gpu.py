@@ -414,3 +414,49 @@ def test_sort_reuse_is_invalidated_by_other_users_of_the_workspace():
     f = T.nfft_forward(y, tp, tb, 4, real_output=True)          # must sort again
     ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
     assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, 4, real_output=True)) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA graphs: the path makes no host synchronisation, allocation or plan creation after its first
+# call (the reference syncs the device after every kernel, csrc/cuda/cuda_utils.cu:7-14), so a
+# transform pair can be captured once and replayed on new data in the same buffers
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,N,m,B,n", [(1, 256, 8, 4, 3000), (3, 32, 4, 2, 4000)])
+def test_cuda_graph_capture_and_replay(d, N, m, B, n):
+    rng = np.random.default_rng(21)
+    pos, batch = make_points(rng, d, B, n)
+    x = make_values(rng, (pos.shape[0], 1), False)
+    tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
+
+    def pair():
+        T.forget_sorted_points()
+        y = T.nfft_adjoint(tx, tp, tb, N, m, batch_size=B)  # batch_size: no batch[-1].item() sync
+        return y, T.nfft_forward(y, tp, tb, m, real_output=True, batch_size=B)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        pair()  # cuFFT plans and the side stream's workspace are created here, outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    before = _lib.launch_count()
+    with torch.cuda.graph(graph, stream=side):
+        gy, gf = pair()
+    captured = _lib.launch_count() - before
+    assert captured > 0
+    # new points and values in the captured buffers; the replay bins the new points on the device
+    pos2 = rng.random(pos.shape, dtype=np.float32) - 0.5
+    x2 = make_values(rng, x.shape, False)
+    tp.copy_(cuda(pos2))
+    tx.copy_(cuda(x2))
+    before = _lib.launch_count()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before  # no host-side launches: the whole pair is one graph launch
+    ref_y = O.nfft_adjoint(x2, pos2, batch, N, m)
+    assert O.rel_l2(gy.cpu().numpy(), ref_y) < TOL
+    assert O.rel_l2(gf.cpu().numpy(), O.nfft_forward(ref_y, pos2, batch, m, real_output=True)) < TOL
+    # eager calls after the replay see the changed tensors (their version moved): no stale sort
+    y3 = T.nfft_adjoint(tx, tp, tb, N, m)
+    assert O.rel_l2(y3.cpu().numpy(), ref_y) < TOL

@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnfft_b200.so")
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SOURCES = ["nfft_b200.cu"]
-_DEPS = ["nfft_b200.cu", "common.cuh", "sort.cuh", "window.cuh", "window_reg.cuh", "window_reg2d.cuh", "spectral.cuh",
+_DEPS = ["nfft_b200.cu", "common.cuh", "sort.cuh", "window.cuh", "window1d.cuh", "window_reg.cuh", "window_reg2d.cuh",
+         "spectral.cuh",
          os.path.join("..", "..", "include", "nfft_b200.h")]
 
 

@@ -149,6 +149,44 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #endif
 }
 
+// Shared-memory loads through an opaque 32-bit shared-window address (-DNFFT_REG_OPAQUE_WIN=1): the
+// compiler cannot rematerialise the per-warp window base inside every point slot (9 instructions per
+// slot in the default build: S2R / S2UR / LDC / ULEA / IMAD ...), it has to keep it in a register.
+template <int K>
+struct IntC { static constexpr int value = K; };
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(addr), "n"(OFF) : "memory");
+    return r;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr), "n"(OFF) : "memory");
+    return r;
+}
+__device__ __forceinline__ float lds_at(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_at(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+template <int BASE, int ZQ, int I = 0>
+__device__ __forceinline__ void lds_window(uint32_t addr, float2* wz) {  // ZQ quads -> 2 ZQ packed pairs
+    if constexpr (I < ZQ) {
+        const float4 w4 = lds_f32x4<BASE + 16 * I>(addr);
+        wz[2 * I] = make_float2(w4.x, w4.y);
+        wz[2 * I + 1] = make_float2(w4.z, w4.w);
+        lds_window<BASE, ZQ, I + 1>(addr, wz);
+    }
+}
+#ifndef NFFT_REG_OPAQUE_WIN
+#define NFFT_REG_OPAQUE_WIN 0
+#endif
+
 inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
     // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
     return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * win_floats * 4 +
@@ -414,6 +452,13 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         wj[q] = ok ? Cfg::XYP + c / WX : 2 * Cfg::XYP - 1;  // y window row (slot 1)
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
+#if NFFT_REG_OPAQUE_WIN
+    uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
+    asm volatile("" : "+r"(wbase));
+    uint32_t awi[CPL], awj[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
+#endif
 
     // work units (columns of supercells or z-ranges of heavy columns) are handed out dynamically
     const int nunits = s_nunits;
@@ -434,6 +479,21 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = make_float2(0.f, 0.f);
+#if NFFT_REG_OPAQUE_WIN >= 2
+        // shared-window byte addresses of this lane's positions in plane 0 of the unit's column: the
+        // add-out then costs one IADD per tile access instead of rebuilding every address from
+        // (lane, coff, scz, sZ) inside the critical section
+        uint32_t aq[CPL];
+        {
+            uint32_t cb = (uint32_t)__cvta_generic_to_shared(cbase);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                aq[q] = cb + 4u * (uint32_t)coff[q];
+                asm volatile("" : "+r"(aq[q]));
+            }
+        }
+        const uint32_t sz4 = 4u * (uint32_t)g.sZ;
+#endif
 
         // Planes 0 .. SZ-1 of the block at supercell `scz` are complete once its points are done:
         // add them out and slide the block up by SZ (all planes when `last`).  Other warps' blocks
@@ -453,6 +513,26 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     }
                     __syncwarp();
                     float2 cur[CPL];
+#if NFFT_REG_OPAQUE_WIN >= 2
+                    (void)pbase;
+                    const uint32_t po = (uint32_t)(scz * SZ + 2 * kp) * sz4;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const bool ok = lane + 32 * q < Cfg::COLS;
+                        cur[q] = make_float2(0.f, 0.f);
+                        if (ok) {
+                            cur[q].x = lds_at(aq[q] + po);
+                            if (two) cur[q].y = lds_at(aq[q] + po + sz4);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        if (lane + 32 * q < Cfg::COLS) {
+                            sts_at(aq[q] + po, cur[q].x + acc[q][kp].x);
+                            if (two) sts_at(aq[q] + po + sz4, cur[q].y + acc[q][kp].y);
+                        }
+                    }
+#else
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
                         const float* src = pbase + coff[q];
@@ -468,6 +548,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                             if (two) dst[g.sZ] = cur[q].y + acc[q][kp].y;
                         }
                     }
+#endif
                     release_fence();
                     __syncwarp();
                     if (lane == 0) atomicExch(lk, 0);
@@ -525,11 +606,37 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                         next_end = s_start[c0 + scz + 1];
                     }
                     const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
+#if NFFT_REG_OPAQUE_WIN
+                    auto point_o = [&](auto kc) {
+                        constexpr int K = decltype(kc)::value;
+                        float w0[CPL], w1[CPL];
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) {
+                            w1[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awj[q]);
+                            w0[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awi[q]);
+                        }
+                        float2 wz[ZP];
+                        lds_window<(kXY + K * Cfg::ZWP) * 4, Cfg::ZQ>(wbase, wz);
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) {
+                            const float v = w1[q] * w0[q];
+                            const float2 vv = make_float2(v, v);
+#pragma unroll
+                            for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
+                        }
+                    };
+#define NFFT_SLOT(K)                                                                       \
+                    case K:                                                                \
+                        point_o(IntC<K>{});                                                \
+                        gp = K + 1;                                                        \
+                        if (K + 1 >= stop) break;
+#else
 #define NFFT_SLOT(K)                                                                       \
                     case K:                                                                \
                         point(win + K * 2 * Cfg::XYP, win + kXY + K * Cfg::ZWP);           \
                         gp = K + 1;                                                        \
                         if (K + 1 >= stop) break;
+#endif
                     switch (gp) {
                         NFFT_SLOT(0) NFFT_SLOT(1) NFFT_SLOT(2) NFFT_SLOT(3)
                         NFFT_SLOT(4) NFFT_SLOT(5) NFFT_SLOT(6) NFFT_SLOT(7)
