@@ -331,24 +331,15 @@ def run_ours(args):
     graph_info = None
     if args.cuda_graph:
         # the same step captured once into a CUDA graph and replayed (no per-launch host cost: matters for
-        # the launch-bound 1D workload c2, 28 launches per pair); reported next to the eager numbers
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(compute_stream)
-        with torch.cuda.stream(side):
-            step_device()
-        compute_stream.wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        l0 = _lib.launch_count()
-        with torch.cuda.graph(graph, stream=side):
-            step_device()
-        captured = _lib.launch_count() - l0
+        # the launch-bound 1D workload c2, 14 kernels per pair); reported next to the eager numbers
+        graphed = T.GraphedTransforms(step_device)
+        graph, captured = graphed.graph, graphed.kernels_per_replay
         for _ in range(3):
             graph.replay()
         ms_graph, _, _ = timed(graph.replay, args.steps)
         graph_info = {"ms_per_step": ms_graph / args.steps, "value": n * world / (ms_graph / args.steps * 1e-3),
                       "unit": "points/s", "kernels_per_replay": int(captured)}
-        del graph
+        del graph, graphed
 
     if args.no_extras:
         ms_e2e = float("nan")

@@ -1,12 +1,13 @@
 #!/bin/bash
-# One GPU session that (1) A/B-times the library variants in gpurun_variants/ on c4, (2) runs the GPU test
+# One GPU session that (1) A/B-times the library variants in gpurun_variants/ on a workload (default c4), (2) runs the GPU test
 # suite, the bench and the ncu passes with the fastest one.  Usage (under gpurun): scripts/final_round.sh [round tag]
 R=${1:-r01b}
+WL=${2:-c4}   # workload the variants are compared on
 mkdir -p gpurun_out
 : > gpurun_out/${R}_ab.txt
 for f in gpurun_variants/lib_*.so; do
-  for rep in 1 2; do
-    v=$(NFFTB200_LIB=$PWD/$f python bench.py --workload c4 --steps 8 --warmup 3 --no-extras 2>>gpurun_out/${R}_ab.err |
+  for rep in 1; do
+    v=$(NFFTB200_LIB=$PWD/$f python bench.py --workload $WL --steps 8 --warmup 3 --no-extras 2>>gpurun_out/${R}_ab.err |
         python -c "import json,sys; d=json.loads(sys.stdin.read().replace('NaN','null')); print('%.4e %s' % (d['value'], json.dumps(d['stage_ms_per_step'])))")
     echo "$f $v" | tee -a gpurun_out/${R}_ab.txt
   done
@@ -36,5 +37,8 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"spread|gather" -s 6 -c 2 -o gpurun_out/${R}_window -f $CMD > gpurun_out/${R}_ncu_window.log 2>&1
 echo "full capture rc=$?"
 python bench.py --workload c2 --steps 50 --warmup 5 --no-extras --cuda-graph > gpurun_out/${R}_bench_c2_graph.json 2>> gpurun_out/${R}_bench.err; cat gpurun_out/${R}_bench_c2_graph.json
+python bench.py --workload c3 --steps 8 --warmup 3 --no-extras > gpurun_out/${R}_bench_c3.json 2>> gpurun_out/${R}_bench.err; cut -c1-300 gpurun_out/${R}_bench_c3.json
 python bench.py --workload c4_clustered --steps 8 --warmup 3 --no-extras > gpurun_out/${R}_bench_c4_clustered.json 2>> gpurun_out/${R}_bench.err; cut -c1-300 gpurun_out/${R}_bench_c4_clustered.json
 python bench.py --impl reference --steps 2 --warmup 1 --ref-points 1048576 > gpurun_out/${R}_bench_ref.json 2> gpurun_out/${R}_bench_ref.err; cut -c1-600 gpurun_out/${R}_bench_ref.json
+C5_LOG2N=23 python scripts/time_c5.py 2>>gpurun_out/${R}_bench.err | tee gpurun_out/${R}_c5.txt
+C5_LOG2N=26 python scripts/time_c5.py 2>>gpurun_out/${R}_bench.err | tee -a gpurun_out/${R}_c5.txt

@@ -123,3 +123,11 @@ def test_adjacency_matrix_rejects_bad_arguments():
         AdjacencyMatrix(W, shift="bogus")
     with pytest.warns(RuntimeWarning):
         AdjacencyMatrix(_Dense(-torch.eye(3)), normalization="sym")
+
+
+def test_graphed_transforms_need_a_gpu():
+    """No CPU fallback anywhere on the hot path: without a CUDA device the graph helper refuses to run."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(RuntimeError):
+        T.GraphedTransforms(lambda: None)

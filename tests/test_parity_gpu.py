@@ -433,25 +433,16 @@ def test_cuda_graph_capture_and_replay(d, N, m, B, n):
         y = T.nfft_adjoint(tx, tp, tb, N, m, batch_size=B)  # batch_size: no batch[-1].item() sync
         return y, T.nfft_forward(y, tp, tb, m, real_output=True, batch_size=B)
 
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        pair()  # cuFFT plans and the side stream's workspace are created here, outside the capture
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    before = _lib.launch_count()
-    with torch.cuda.graph(graph, stream=side):
-        gy, gf = pair()
-    captured = _lib.launch_count() - before
-    assert captured > 0
+    graphed = T.GraphedTransforms(pair)  # warm-up on a side stream (plans, workspace), then the capture
+    gy, gf = graphed.outputs
+    assert graphed.kernels_per_replay > 0
     # new points and values in the captured buffers; the replay bins the new points on the device
     pos2 = rng.random(pos.shape, dtype=np.float32) - 0.5
     x2 = make_values(rng, x.shape, False)
     tp.copy_(cuda(pos2))
     tx.copy_(cuda(x2))
     before = _lib.launch_count()
-    graph.replay()
+    assert graphed.replay()[0] is gy
     torch.cuda.synchronize()
     assert _lib.launch_count() == before  # no host-side launches: the whole pair is one graph launch
     ref_y = O.nfft_adjoint(x2, pos2, batch, N, m)

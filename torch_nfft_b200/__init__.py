@@ -13,5 +13,6 @@ from .coeffs import gaussian_analytic_coeffs, gaussian_interpolated_coeffs, \
     interpolation_grid, radial_interpolation_grid, interpolated_kernel_coeffs
 from .matrices import GramMatrix, AdjacencyMatrix
 from .kernel import GaussianKernel
+from .graph import GraphedTransforms
 
 __version__ = "0.1.0"

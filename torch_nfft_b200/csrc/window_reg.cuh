@@ -174,6 +174,23 @@ __device__ __forceinline__ float lds_at(uint32_t addr) {
 __device__ __forceinline__ void sts_at(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion is awaited with
+// cp_async_wait_all() before the CTA barrier that publishes the tile
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {  // both 16-byte aligned
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+#ifndef NFFT_REG_ASYNC_TILE
+#define NFFT_REG_ASYNC_TILE 1
+#endif
+#ifndef NFFT_REG_GSLOTTED
+#define NFFT_REG_GSLOTTED 1
+#endif
 template <int BASE, int ZQ, int I = 0>
 __device__ __forceinline__ void lds_window(uint32_t addr, float2* wz) {  // ZQ quads -> 2 ZQ packed pairs
     if constexpr (I < ZQ) {
@@ -184,7 +201,7 @@ __device__ __forceinline__ void lds_window(uint32_t addr, float2* wz) {  // ZQ q
     }
 }
 #ifndef NFFT_REG_OPAQUE_WIN
-#define NFFT_REG_OPAQUE_WIN 0
+#define NFFT_REG_OPAQUE_WIN 3
 #endif
 
 inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
@@ -738,16 +755,37 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     __shared__ int s_order[64], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     // stage the padded tile (periodic wrap resolved per quad)
+#if NFFT_REG_ASYNC_TILE
+    // the tile travels with asynchronous copies while the points are loaded and bucketed (both phases
+    // are latency-bound); complex grids: this pass's component of the interleaved pairs
+    {
+        const int cs = g.cplx ? 2 : 1;
+        const float* gsrc = a.grid + grid_plane(g, t.b, a.k0) + (g.cplx ? (a.k0 & 1) : 0);
+        const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+        for_each_quad<3>(g, t, [&](int so, long long cell) {
+            const float* src = gsrc + cs * cell;
+            const uint32_t dst = tile_s + 4u * (uint32_t)so;
+            cp_async4(dst, src);
+            cp_async4(dst + 4, src + cs);
+            cp_async4(dst + 8, src + 2 * cs);
+            cp_async4(dst + 12, src + 3 * cs);
+        });
+    }
+#else
     for_each_quad<3>(g, t, [&](int so, long long cell) {
         const float4 val = load_quad(g, a.grid, t.b, a.k0, cell);
         float* s = tile + so;
         s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
     });
+#endif
     __syncthreads();
     NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
+#if NFFT_REG_ASYNC_TILE
+    cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
+#endif
     make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(1, 5, ph0, pha);
@@ -768,6 +806,13 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         wj[q] = ok ? Cfg::XYP + c / WX : 2 * Cfg::XYP - 1;  // y window row (slot 1)
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
+#if NFFT_REG_OPAQUE_WIN >= 3 && NFFT_REG_GSLOTTED
+    uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
+    asm volatile("" : "+r"(wbase));
+    uint32_t awi[CPL], awj[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
+#endif
     // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
     const int zmax = g.P[2] - 1;
 
@@ -793,6 +838,37 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         // register block: planes [scz*SZ, scz*SZ + 2 ZP) of the column; loaded at the unit's first
         // populated supercell, then slid
         float2 blk[CPL][ZP];
+#if NFFT_REG_OPAQUE_WIN >= 3
+        // shared-window byte addresses of this lane's positions in plane 0 of the unit's column (see the
+        // spread kernel): a block load is one IADD + LDS per cell
+        uint32_t aq[CPL];
+        {
+            const uint32_t cb = (uint32_t)__cvta_generic_to_shared(cbase);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                aq[q] = cb + 4u * (uint32_t)coff[q];
+                asm volatile("" : "+r"(aq[q]));
+            }
+        }
+        const uint32_t sz4 = 4u * (uint32_t)g.sZ;
+        auto load_pair = [&](int kp, int scz) {  // planes scz*SZ + 2 kp, + 1 of every position (clamped)
+            const int z0 = scz * SZ + 2 * kp;
+            const uint32_t oa = (uint32_t)(z0 < zmax ? z0 : zmax) * sz4, ob = (uint32_t)(z0 + 1 < zmax ? z0 + 1 : zmax) * sz4;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) blk[q][kp] = make_float2(lds_at(aq[q] + oa), lds_at(aq[q] + ob));
+        };
+#pragma unroll
+        for (int kp = 0; kp < ZP; ++kp) load_pair(kp, scz);
+        auto advance = [&](int scz) {
+#pragma unroll
+            for (int kp = 0; kp + SP < ZP; ++kp)
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) blk[q][kp] = blk[q][kp + SP];
+#pragma unroll
+            for (int kp = ZP - SP; kp < ZP; ++kp) load_pair(kp, scz);
+        };
+        auto advance_unused = [&](int scz) {
+#else
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
@@ -803,6 +879,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
             }
         // move the block to supercell `scz`: slide down by SZ and load the SZ new top planes
         auto advance = [&](int scz) {
+#endif
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
 #pragma unroll
@@ -817,6 +894,9 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                 }
             }
         };
+#if NFFT_REG_OPAQUE_WIN >= 3
+        (void)advance_unused;
+#endif
 
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
@@ -826,6 +906,96 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
             // the round is evaluated in sub-rounds of kGatherSlots unrolled point slots (static registers
             // for the partial sums): 8 slots in one go make the hot loop larger than the instruction cache
             // likes (every slot carries a copy of the block slide)
+#if NFFT_REG_GSLOTTED
+            // As in the spread: one copy of the point body per slot (window loads with immediate offsets, the
+            // partial sum in a static register), entered through a switch; a slot that ends a supercell
+            // leaves the switch so that the ONE copy of the block slide above it runs.  (The unrolled loop
+            // below carries a copy of the slide in every slot: 8 x 140 instructions.)
+            static_assert(!NFFT_REG_GSLOTTED || (kGatherSlots == 8 && kRegGroup == 8), "slotted gather: 8 slots");
+            float part[kGatherSlots];
+#pragma unroll
+            for (int sl = 0; sl < kGatherSlots; ++sl) part[sl] = 0.f;
+            auto gpoint = [&](const float* wv, const float* wzp) {
+                float2 wz[ZP];
+#pragma unroll
+                for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
+                    const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
+                    wz[2 * l4] = make_float2(w4.x, w4.y);
+                    wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
+                }
+                float2 zsum[ZP];
+#pragma unroll
+                for (int kp = 0; kp < ZP; ++kp) zsum[kp] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const float w = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X)
+                    const float2 ww = make_float2(w, w);
+#pragma unroll
+                    for (int kp = 0; kp < ZP; ++kp) zsum[kp] = ffma2(ww, blk[q][kp], zsum[kp]);
+                }
+                float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int kp = 0; kp < ZP; ++kp) sum = ffma2(wz[kp], zsum[kp], sum);
+                asm volatile("" ::: "memory");  // keeps the next slot's loads from being hoisted
+                return sum.x + sum.y;
+            };
+            for (int gp = 0; gp < npts;) {
+                while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
+                    ++scz;
+                    advance(scz);
+                    next_end = s_start[c0 + scz + 1];
+                }
+                const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
+#if NFFT_REG_OPAQUE_WIN >= 3
+                auto gpoint_o = [&](auto kc) {
+                    constexpr int K = decltype(kc)::value;
+                    float w0[CPL], w1[CPL];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        w1[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awj[q]);
+                        w0[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awi[q]);
+                    }
+                    float2 wz[ZP];
+                    lds_window<(kXY + K * Cfg::ZWP) * 4, Cfg::ZQ>(wbase, wz);
+                    float2 zsum[ZP];
+#pragma unroll
+                    for (int kp = 0; kp < ZP; ++kp) zsum[kp] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const float w = w1[q] * w0[q];  // psi(Y) * psi(X)
+                        const float2 ww = make_float2(w, w);
+#pragma unroll
+                        for (int kp = 0; kp < ZP; ++kp) zsum[kp] = ffma2(ww, blk[q][kp], zsum[kp]);
+                    }
+                    float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int kp = 0; kp < ZP; ++kp) sum = ffma2(wz[kp], zsum[kp], sum);
+                    return sum.x + sum.y;
+                };
+#define NFFT_GSLOT(K)                                                                      \
+                case K:                                                                    \
+                    part[K] = gpoint_o(IntC<K>{});                                         \
+                    gp = K + 1;                                                            \
+                    if (K + 1 >= stop) break;
+#else
+#define NFFT_GSLOT(K)                                                                      \
+                case K:                                                                    \
+                    part[K] = gpoint(win + K * 2 * Cfg::XYP, win + kXY + K * Cfg::ZWP);    \
+                    gp = K + 1;                                                            \
+                    if (K + 1 >= stop) break;
+#endif
+                switch (gp) {
+                    NFFT_GSLOT(0) NFFT_GSLOT(1) NFFT_GSLOT(2) NFFT_GSLOT(3)
+                    NFFT_GSLOT(4) NFFT_GSLOT(5) NFFT_GSLOT(6) NFFT_GSLOT(7)
+                    default: break;
+                }
+#undef NFFT_GSLOT
+            }
+            (void)wv;
+            (void)wzp;
+            {
+            const int g0 = 0;
+#else
 #pragma unroll 1
             for (int g0 = 0; g0 < npts; g0 += kGatherSlots) {
             float part[kGatherSlots];
@@ -877,6 +1047,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                     part[sl] = sum.x + sum.y;
                 }
             }
+#endif
             // sum the partials over the warp (transpose reduction: 9 shuffles for 8 values, 7 for 4);
             // lane (32 / kGatherSlots) p then holds the value of point g0 + p
             warp_reduce_channels<kGatherSlots>(part, lane);
