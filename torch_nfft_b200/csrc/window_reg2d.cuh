@@ -14,10 +14,10 @@
 #define NFFT_REG2_FFMA2 1
 #endif
 #ifndef NFFT_REG2_UNROLL
-#define NFFT_REG2_UNROLL 0
+#define NFFT_REG2_UNROLL 1
 #endif
 #ifndef NFFT_REG2_ASYNC_TILE
-#define NFFT_REG2_ASYNC_TILE 0
+#define NFFT_REG2_ASYNC_TILE 1
 #endif
 #ifndef NFFT_REG2_BANDED
 #define NFFT_REG2_BANDED 1
