@@ -210,8 +210,12 @@ struct IntC { static constexpr int value = K; };
 // steps through the (y, z) rows, so that an iteration costs two wraps and four multiply-adds instead of
 // two divisions and three integer modulo operations (ncu source view of the previous flush: 145
 // instructions per quad, 11.7 % of all warp instructions of the spread kernel).
+#ifndef NFFT_REG_WALK_UNROLL
+#define NFFT_REG_WALK_UNROLL 1
+#endif
+constexpr int kWalkUnroll = NFFT_REG_WALK_UNROLL;
 #ifndef NFFT_REG_ROWQUADS
-#define NFFT_REG_ROWQUADS 0
+#define NFFT_REG_ROWQUADS 1
 #endif
 template <typename F>
 __device__ __forceinline__ void for_each_quad3_rows(const Geom& g, const TileCtx& t, F f) {
@@ -238,6 +242,11 @@ __device__ __forceinline__ void for_each_quad3_rows(const Geom& g, const TileCtx
         auto wrap = [&](int v) { return kPow2 ? (v & (M - 1)) : wrap_mod(v, M); };
         const int gx = wrap(t.org[0] + x);
         int y = y0, z = z0;
+        // unrolled: consecutive quads use different registers, so a quad's loads do not wait for the
+        // previous quad's global reduction to have read its operands (long-scoreboard stalls of the flush)
+#if NFFT_REG_WALK_UNROLL > 1
+#pragma unroll kWalkUnroll
+#endif
         for (int row = row0; row < rows; row += rstep) {
             const int gy = wrap(t.org[1] + y), gz = wrap(t.org[2] + z);
             const long long cell = (long long)(gz * M + gy) * M + gx;
