@@ -33,25 +33,9 @@ constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) hel
 #ifndef NFFT_REG_FFMA2
 #define NFFT_REG_FFMA2 1
 #endif
-constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round (a power of two <= 32 / 3 lanes... 8)
-static_assert(kRegGroup == 8 || kRegGroup == 4 || kRegGroup == 2, "the gather reduction needs a power of two; 3 * kRegGroup <= 32");
-#ifndef NFFT_REG_SCALEZ
-#define NFFT_REG_SCALEZ 1
-#endif
-#ifndef NFFT_REG_GATHER_ORDER
-#define NFFT_REG_GATHER_ORDER 1
-#endif
-#ifndef NFFT_REG_GSLOTS
-#define NFFT_REG_GSLOTS 8
-#endif
-constexpr int kGatherSlots = NFFT_REG_GSLOTS;  // unrolled point slots of the gather (a power of two <= kRegGroup)
-#ifndef NFFT_REG_SLOTTED
-#define NFFT_REG_SLOTTED 1
-#endif
-#ifndef NFFT_REG_PTUNROLL
-#define NFFT_REG_PTUNROLL 2
-#endif
-constexpr int kPtUnroll = NFFT_REG_PTUNROLL;  // unroll factor of the spread point loop
+constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round: one lane per (point, dimension), 3 * 8 <= 32
+static_assert(kRegGroup == 8, "the sweeps have one point body per slot of an 8-point round");
+constexpr int kGatherSlots = 8;  // point slots of a gather round (= kRegGroup)
 
 // Debug build (-DNFFT_PHASE_TIMING): thread 0 of every CTA adds the clock64() length of its phases to
 // g_phase[kernel][phase]; read back through nfftb200_debug_phase_read.  Phases: 0 zero + bucket +
@@ -149,9 +133,10 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #endif
 }
 
-// Shared-memory loads through an opaque 32-bit shared-window address (-DNFFT_REG_OPAQUE_WIN=1): the
-// compiler cannot rematerialise the per-warp window base inside every point slot (9 instructions per
-// slot in the default build: S2R / S2UR / LDC / ULEA / IMAD ...), it has to keep it in a register.
+// Shared-memory accesses of the sweeps go through opaque 32-bit shared-window addresses
+// (`asm volatile("" : "+r"(addr))` + ld/st.shared): at 128 registers ptxas otherwise rematerialises the
+// per-warp window base inside every point slot (S2R / S2UR / LDC / ULEA / IMAD: 9 of 69 instructions)
+// and rebuilds every tile address of the add-out inside its critical section (175 -> 113 instructions).
 template <int OFF>
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float r;
@@ -183,12 +168,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {  //
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
-#ifndef NFFT_REG_ASYNC_TILE
-#define NFFT_REG_ASYNC_TILE 1
-#endif
-#ifndef NFFT_REG_GSLOTTED
-#define NFFT_REG_GSLOTTED 1
-#endif
 template <int BASE, int ZQ, int I = 0>
 __device__ __forceinline__ void lds_window(uint32_t addr, float2* wz) {  // ZQ quads -> 2 ZQ packed pairs
     if constexpr (I < ZQ) {
@@ -198,9 +177,6 @@ __device__ __forceinline__ void lds_window(uint32_t addr, float2* wz) {  // ZQ q
         lds_window<BASE, ZQ, I + 1>(addr, wz);
     }
 }
-#ifndef NFFT_REG_OPAQUE_WIN
-#define NFFT_REG_OPAQUE_WIN 3
-#endif
 
 template <int K>
 struct IntC { static constexpr int value = K; };
@@ -214,12 +190,8 @@ struct IntC { static constexpr int value = K; };
 #define NFFT_REG_WALK_UNROLL 1
 #endif
 constexpr int kWalkUnroll = NFFT_REG_WALK_UNROLL;
-#ifndef NFFT_REG_ROWQUADS
-#define NFFT_REG_ROWQUADS 1
-#endif
 template <typename F>
 __device__ __forceinline__ void for_each_quad3_rows(const Geom& g, const TileCtx& t, F f) {
-#if NFFT_REG_ROWQUADS
     const int nx4 = g.P[0] >> 2;
     int shift = 0;
     while ((1 << shift) < nx4) ++shift;                    // lanes per row: the next power of two
@@ -261,9 +233,6 @@ __device__ __forceinline__ void for_each_quad3_rows(const Geom& g, const TileCtx
     };
     if ((M & (M - 1)) == 0) walk(IntC<1>{});
     else walk(IntC<0>{});
-#else
-    for_each_quad<3>(g, t, f);
-#endif
 }
 
 inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
@@ -531,13 +500,11 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         wj[q] = ok ? Cfg::XYP + c / WX : 2 * Cfg::XYP - 1;  // y window row (slot 1)
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
-#if NFFT_REG_OPAQUE_WIN
     uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
     asm volatile("" : "+r"(wbase));
     uint32_t awi[CPL], awj[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
-#endif
 
     // work units (columns of supercells or z-ranges of heavy columns) are handed out dynamically
     const int nunits = s_nunits;
@@ -558,7 +525,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         for (int q = 0; q < CPL; ++q)
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = make_float2(0.f, 0.f);
-#if NFFT_REG_OPAQUE_WIN >= 2
         // shared-window byte addresses of this lane's positions in plane 0 of the unit's column: the
         // add-out then costs one IADD per tile access instead of rebuilding every address from
         // (lane, coff, scz, sZ) inside the critical section
@@ -572,7 +538,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
             }
         }
         const uint32_t sz4 = 4u * (uint32_t)g.sZ;
-#endif
 
         // Planes 0 .. SZ-1 of the block at supercell `scz` are complete once its points are done:
         // add them out and slide the block up by SZ (all planes when `last`).  Other warps' blocks
@@ -584,7 +549,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
             for (int kp = 0; kp < ZP; ++kp) {
                 if ((kp < SP || last) && 2 * kp < zlim) {
-                    float* pbase = cbase + (scz * SZ + 2 * kp) * g.sZ;
                     const bool two = 2 * kp + 1 < zlim;
                     int* lk = s_lock + scz * SP + kp;
                     if (lane == 0) {
@@ -592,8 +556,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     }
                     __syncwarp();
                     float2 cur[CPL];
-#if NFFT_REG_OPAQUE_WIN >= 2
-                    (void)pbase;
                     const uint32_t po = (uint32_t)(scz * SZ + 2 * kp) * sz4;
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
@@ -611,23 +573,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                             if (two) sts_at(aq[q] + po + sz4, cur[q].y + acc[q][kp].y);
                         }
                     }
-#else
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const float* src = pbase + coff[q];
-                        const bool ok = lane + 32 * q < Cfg::COLS;
-                        cur[q].x = ok ? src[0] : 0.f;
-                        cur[q].y = ok && two ? src[g.sZ] : 0.f;
-                    }
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        float* dst = pbase + coff[q];
-                        if (lane + 32 * q < Cfg::COLS) {
-                            dst[0] = cur[q].x + acc[q][kp].x;
-                            if (two) dst[g.sZ] = cur[q].y + acc[q][kp].y;
-                        }
-                    }
-#endif
                     release_fence();
                     __syncwarp();
                     if (lane == 0) atomicExch(lk, 0);
@@ -651,33 +596,12 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
             }
             for (int base = lo_seg; base < hi_seg; base += kRegGroup) {
                 const int npts = hi_seg - base < kRegGroup ? hi_seg - base : kRegGroup;
-                stage_windows<Cfg, LC, NFFT_REG_SCALEZ>(g, s_pts, s_off, base, npts, win, lane, pow2);
-                const float* wv = win;          // x / y windows of the point
-                const float* wzp = win + kXY;   // z window of the point
-#if NFFT_REG_SLOTTED
+                stage_windows<Cfg, LC, true>(g, s_pts, s_off, base, npts, win, lane, pow2);
                 // One copy of the point body per slot of the round (window loads with immediate offsets),
                 // entered through a switch; a slot that ends a supercell leaves the switch so that the ONE
                 // copy of the add-out code above it runs, and the switch is re-entered at the next slot.
-                auto point = [&](const float* wv, const float* wzp) {
-                    float2 wz[ZP];
-#pragma unroll
-                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                        const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
-                        wz[2 * l4] = make_float2(w4.x, w4.y);
-                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                    }
-                    float v[CPL];
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) v[q] = wv[wj[q]] * wv[wi[q]];  // x value folded into wz
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const float2 vv = make_float2(v[q], v[q]);
-#pragma unroll
-                        for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
-                    }
-                    asm volatile("" ::: "memory");  // keeps the next slot's loads from being hoisted
-                };
-                static_assert(!NFFT_REG_SLOTTED || (NFFT_REG_SCALEZ && kRegGroup == 8), "slotted sweep: 8 slots, value in wz");
+                // The z window carries the point's value (stage_windows<.., true>).
+                static_assert(kRegGroup == 8, "slotted sweep: 8 slots");
                 for (int gp = 0; gp < npts;) {
                     while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
                         advance(scz, false);
@@ -685,8 +609,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                         next_end = s_start[c0 + scz + 1];
                     }
                     const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
-#if NFFT_REG_OPAQUE_WIN
-                    auto point_o = [&](auto kc) {
+                    auto point = [&](auto kc) {
                         constexpr int K = decltype(kc)::value;
                         float w0[CPL], w1[CPL];
 #pragma unroll
@@ -706,16 +629,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     };
 #define NFFT_SLOT(K)                                                                       \
                     case K:                                                                \
-                        point_o(IntC<K>{});                                                \
+                        point(IntC<K>{});                                                \
                         gp = K + 1;                                                        \
                         if (K + 1 >= stop) break;
-#else
-#define NFFT_SLOT(K)                                                                       \
-                    case K:                                                                \
-                        point(win + K * 2 * Cfg::XYP, win + kXY + K * Cfg::ZWP);           \
-                        gp = K + 1;                                                        \
-                        if (K + 1 >= stop) break;
-#endif
                     switch (gp) {
                         NFFT_SLOT(0) NFFT_SLOT(1) NFFT_SLOT(2) NFFT_SLOT(3)
                         NFFT_SLOT(4) NFFT_SLOT(5) NFFT_SLOT(6) NFFT_SLOT(7)
@@ -723,46 +639,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     }
 #undef NFFT_SLOT
                 }
-#else
-#pragma unroll kPtUnroll
-                for (int gp = 0; gp < npts; ++gp, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
-                    while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
-                        advance(scz, false);
-                        ++scz;
-                        next_end = s_start[c0 + scz + 1];
-                    }
-#if !NFFT_REG_SCALEZ
-                    const float xval = s_pts[base + gp].w;
-#endif
-                    float2 wz[ZP];
-#pragma unroll
-                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                        const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
-                        wz[2 * l4] = make_float2(w4.x, w4.y);
-                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                    }
-                    float v[CPL];
-#pragma unroll
-#if NFFT_REG_SCALEZ
-                    for (int q = 0; q < CPL; ++q) v[q] = wv[wj[q]] * wv[wi[q]];  // x value folded into wz
-#else
-                    for (int q = 0; q < CPL; ++q) v[q] = (xval * wv[wj[q]]) * wv[wi[q]];
-#endif
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const float2 vv = make_float2(v[q], v[q]);
-#pragma unroll
-                        for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
-                    }
-#if NFFT_REG_PTUNROLL > 1
-                    // unrolled point loop: half of the window loads get immediate offsets; the barrier keeps
-                    // the compiler from hoisting the next point's loads (register pressure).  Measured at
-                    // c4: 4.36 ms rolled, 4.28 ms by 2; by 4 or 8 the copies of the add-out code thrash
-                    // the instruction cache (6.1 / 9.6 ms).
-                    asm volatile("" ::: "memory");
-#endif
-                }
-#endif
                 __syncwarp();
             }
             // the unit's last point lies in supercell scz: everything the block holds goes out
@@ -817,7 +693,6 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     __shared__ int s_order[64], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     // stage the padded tile (periodic wrap resolved per quad)
-#if NFFT_REG_ASYNC_TILE
     // the tile travels with asynchronous copies while the points are loaded and bucketed (both phases
     // are latency-bound); complex grids: this pass's component of the interleaved pairs
     {
@@ -833,21 +708,12 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
             cp_async4(dst + 12, src + 3 * cs);
         });
     }
-#else
-    for_each_quad3_rows(g, t, [&](int so, long long cell) {
-        const float4 val = load_quad(g, a.grid, t.b, a.k0, cell);
-        float* s = tile + so;
-        s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
-    });
-#endif
     __syncthreads();
     NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-#if NFFT_REG_ASYNC_TILE
     cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
-#endif
     make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(1, 5, ph0, pha);
@@ -868,13 +734,11 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         wj[q] = ok ? Cfg::XYP + c / WX : 2 * Cfg::XYP - 1;  // y window row (slot 1)
         coff[q] = ok ? (c / WX) * g.sY + (c % WX) : 0;
     }
-#if NFFT_REG_OPAQUE_WIN >= 3 && NFFT_REG_GSLOTTED
     uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
     asm volatile("" : "+r"(wbase));
     uint32_t awi[CPL], awj[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
-#endif
     // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
     const int zmax = g.P[2] - 1;
 
@@ -900,7 +764,6 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         // register block: planes [scz*SZ, scz*SZ + 2 ZP) of the column; loaded at the unit's first
         // populated supercell, then slid
         float2 blk[CPL][ZP];
-#if NFFT_REG_OPAQUE_WIN >= 3
         // shared-window byte addresses of this lane's positions in plane 0 of the unit's column (see the
         // spread kernel): a block load is one IADD + LDS per cell
         uint32_t aq[CPL];
@@ -929,78 +792,18 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
             for (int kp = ZP - SP; kp < ZP; ++kp) load_pair(kp, scz);
         };
-        auto advance_unused = [&](int scz) {
-#else
-#pragma unroll
-        for (int q = 0; q < CPL; ++q)
-#pragma unroll
-            for (int kp = 0; kp < ZP; ++kp) {
-                const int z0 = scz * SZ + 2 * kp;
-                const int za = z0 < zmax ? z0 : zmax, zb = z0 + 1 < zmax ? z0 + 1 : zmax;
-                blk[q][kp] = make_float2(cbase[za * g.sZ + coff[q]], cbase[zb * g.sZ + coff[q]]);
-            }
-        // move the block to supercell `scz`: slide down by SZ and load the SZ new top planes
-        auto advance = [&](int scz) {
-#endif
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-#pragma unroll
-                for (int kp = 0; kp < ZP; ++kp) {
-                    if (kp + SP < ZP) {
-                        blk[q][kp] = blk[q][kp + SP];
-                    } else {
-                        const int z0 = scz * SZ + 2 * kp;
-                        const int za = z0 < zmax ? z0 : zmax, zb = z0 + 1 < zmax ? z0 + 1 : zmax;
-                        blk[q][kp] = make_float2(cbase[za * g.sZ + coff[q]], cbase[zb * g.sZ + coff[q]]);
-                    }
-                }
-            }
-        };
-#if NFFT_REG_OPAQUE_WIN >= 3
-        (void)advance_unused;
-#endif
 
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
             stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
-            const float* wv = win;
-            const float* wzp = win + kXY;
-            // the round is evaluated in sub-rounds of kGatherSlots unrolled point slots (static registers
-            // for the partial sums): 8 slots in one go make the hot loop larger than the instruction cache
-            // likes (every slot carries a copy of the block slide)
-#if NFFT_REG_GSLOTTED
             // As in the spread: one copy of the point body per slot (window loads with immediate offsets, the
             // partial sum in a static register), entered through a switch; a slot that ends a supercell
-            // leaves the switch so that the ONE copy of the block slide above it runs.  (The unrolled loop
-            // below carries a copy of the slide in every slot: 8 x 140 instructions.)
-            static_assert(!NFFT_REG_GSLOTTED || (kGatherSlots == 8 && kRegGroup == 8), "slotted gather: 8 slots");
+            // leaves the switch so that the ONE copy of the block slide runs.  (An unrolled loop carries a
+            // copy of the slide in every slot: 8 x 140 instructions, instruction-cache misses.)
+            static_assert(kGatherSlots == 8 && kRegGroup == 8, "slotted gather: 8 slots");
             float part[kGatherSlots];
 #pragma unroll
             for (int sl = 0; sl < kGatherSlots; ++sl) part[sl] = 0.f;
-            auto gpoint = [&](const float* wv, const float* wzp) {
-                float2 wz[ZP];
-#pragma unroll
-                for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                    const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
-                    wz[2 * l4] = make_float2(w4.x, w4.y);
-                    wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                }
-                float2 zsum[ZP];
-#pragma unroll
-                for (int kp = 0; kp < ZP; ++kp) zsum[kp] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) {
-                    const float w = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X)
-                    const float2 ww = make_float2(w, w);
-#pragma unroll
-                    for (int kp = 0; kp < ZP; ++kp) zsum[kp] = ffma2(ww, blk[q][kp], zsum[kp]);
-                }
-                float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int kp = 0; kp < ZP; ++kp) sum = ffma2(wz[kp], zsum[kp], sum);
-                asm volatile("" ::: "memory");  // keeps the next slot's loads from being hoisted
-                return sum.x + sum.y;
-            };
             for (int gp = 0; gp < npts;) {
                 while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
                     ++scz;
@@ -1008,8 +811,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                     next_end = s_start[c0 + scz + 1];
                 }
                 const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
-#if NFFT_REG_OPAQUE_WIN >= 3
-                auto gpoint_o = [&](auto kc) {
+                auto gpoint = [&](auto kc) {
                     constexpr int K = decltype(kc)::value;
                     float w0[CPL], w1[CPL];
 #pragma unroll
@@ -1036,16 +838,9 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                 };
 #define NFFT_GSLOT(K)                                                                      \
                 case K:                                                                    \
-                    part[K] = gpoint_o(IntC<K>{});                                         \
+                    part[K] = gpoint(IntC<K>{});                                         \
                     gp = K + 1;                                                            \
                     if (K + 1 >= stop) break;
-#else
-#define NFFT_GSLOT(K)                                                                      \
-                case K:                                                                    \
-                    part[K] = gpoint(win + K * 2 * Cfg::XYP, win + kXY + K * Cfg::ZWP);    \
-                    gp = K + 1;                                                            \
-                    if (K + 1 >= stop) break;
-#endif
                 switch (gp) {
                     NFFT_GSLOT(0) NFFT_GSLOT(1) NFFT_GSLOT(2) NFFT_GSLOT(3)
                     NFFT_GSLOT(4) NFFT_GSLOT(5) NFFT_GSLOT(6) NFFT_GSLOT(7)
@@ -1053,72 +848,14 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
                 }
 #undef NFFT_GSLOT
             }
-            (void)wv;
-            (void)wzp;
-            {
-            const int g0 = 0;
-#else
-#pragma unroll 1
-            for (int g0 = 0; g0 < npts; g0 += kGatherSlots) {
-            float part[kGatherSlots];
-#pragma unroll
-            for (int sl = 0; sl < kGatherSlots; ++sl) part[sl] = 0.f;
-#pragma unroll
-            for (int sl = 0; sl < kGatherSlots; ++sl, wv += 2 * Cfg::XYP, wzp += Cfg::ZWP) {
-                const int gp = g0 + sl;
-                if (gp < npts) {
-                    while (base + gp >= next_end) {  // warp-uniform: the sweep reaches the next supercell
-                        ++scz;
-                        advance(scz);
-                        next_end = s_start[c0 + scz + 1];
-                    }
-                    float2 wz[ZP];
-#pragma unroll
-                    for (int l4 = 0; l4 < Cfg::ZQ; ++l4) {
-                        const float4 w4 = reinterpret_cast<const float4*>(wzp)[l4];
-                        wz[2 * l4] = make_float2(w4.x, w4.y);
-                        wz[2 * l4 + 1] = make_float2(w4.z, w4.w);
-                    }
-#if NFFT_REG_GATHER_ORDER
-                    // sum over the (x, y) positions first (scalar-broadcast FFMA2, ZP independent
-                    // chains), then over z
-                    float2 zsum[ZP];
-#pragma unroll
-                    for (int kp = 0; kp < ZP; ++kp) zsum[kp] = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const float w = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X)
-                        const float2 ww = make_float2(w, w);
-#pragma unroll
-                        for (int kp = 0; kp < ZP; ++kp) zsum[kp] = ffma2(ww, blk[q][kp], zsum[kp]);
-                    }
-                    float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int kp = 0; kp < ZP; ++kp) sum = ffma2(wz[kp], zsum[kp], sum);
-#else
-                    float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const float w = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X)
-                        float2 inner = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int kp = 0; kp < ZP; ++kp) inner = ffma2(wz[kp], blk[q][kp], inner);
-                        sum = ffma2(make_float2(w, w), inner, sum);
-                    }
-#endif
-                    part[sl] = sum.x + sum.y;
-                }
-            }
-#endif
-            // sum the partials over the warp (transpose reduction: 9 shuffles for 8 values, 7 for 4);
-            // lane (32 / kGatherSlots) p then holds the value of point g0 + p
+            // sum the partials over the warp (transpose reduction: 9 shuffles for 8 values);
+            // lane (32 / kGatherSlots) p then holds the value of point p of the round
             warp_reduce_channels<kGatherSlots>(part, lane);
             constexpr int kLanesPerPoint = 32 / kGatherSlots;
-            if ((lane & (kLanesPerPoint - 1)) == 0 && g0 + lane / kLanesPerPoint < npts) {
-                const int gp = g0 + lane / kLanesPerPoint;
+            if ((lane & (kLanesPerPoint - 1)) == 0 && lane / kLanesPerPoint < npts) {
+                const int gp = lane / kLanesPerPoint;
                 const uint32_t i = (uint32_t)__float_as_int(s_pts[base + gp].w);
                 a.yout[(size_t)i * g.K + a.k0] = part[0];
-            }
             }
             __syncwarp();
         }

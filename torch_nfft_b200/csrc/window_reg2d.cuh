@@ -13,12 +13,6 @@
 #ifndef NFFT_REG2_FFMA2
 #define NFFT_REG2_FFMA2 1
 #endif
-#ifndef NFFT_REG2_UNROLL
-#define NFFT_REG2_UNROLL 1
-#endif
-#ifndef NFFT_REG2_ASYNC_TILE
-#define NFFT_REG2_ASYNC_TILE 1
-#endif
 #ifndef NFFT_REG2_BANDED
 #define NFFT_REG2_BANDED 1
 #endif
@@ -225,15 +219,11 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
             stage_windows_2d<Cfg, LC, PITCH, POS>(g, s_rec, s_off, base, npts, win, lane, pow2);
             const float* wv0 = win;
             const float* rec0 = s_rec + (size_t)base * PITCH;
-#if NFFT_REG2_UNROLL
             // one copy of the point body per slot of the round: the 12 window loads get immediate offsets
             // instead of 12 address additions per point (60 -> 44 instructions per point with 8 channels)
 #pragma unroll
             for (int gp = 0; gp < kReg2Group; ++gp) {
                 if (gp >= npts) break;
-#else
-            for (int gp = 0; gp < npts; ++gp) {
-#endif
                 const float* wv = wv0 + gp * 2 * Cfg::XYP;
                 const float* rec = rec0 + gp * PITCH;
                 float xs[NCOMP];
@@ -361,7 +351,6 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
 
     for (int i = threadIdx.x; i < nsc; i += kReg2Threads) s_cur[i] = 0;
     if (threadIdx.x == 0) s_next = 0;
-#if NFFT_REG2_ASYNC_TILE
     // the tile planes travel with asynchronous copies (16 bytes per quad when the tile strides keep the
     // quads aligned, else 4 x 4 bytes) while the points are loaded and bucketed
     {
@@ -389,23 +378,10 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
             }
         });
     }
-#else
-    for_each_quad<2>(g, t, [&](int so, long long cell) {
-#pragma unroll
-        for (int k = 0; k < NCOMP; ++k) {
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.k0 + k < g.K) val = load_quad(g, a.grid, t.b, a.k0 + k, cell);
-            float* s = tile + (size_t)k * g.tile_elems + so;
-            s[0] = val.x; s[1] = val.y; s[2] = val.z; s[3] = val.w;
-        }
-    });
-#endif
     __syncthreads();
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points_2d<NCOMP, false, PITCH, POS>(g, a, t, cnt, nsx, nsy, s_rec, s_off, s_start, s_cur);
-#if NFFT_REG2_ASYNC_TILE
     cp_async_wait_all();  // order_columns ends with a barrier, which publishes the tile
-#endif
     order_columns(s_start, nsc, 1, s_order);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,13 +420,9 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
             const int npts = hi - base < kReg2Group ? hi - base : kReg2Group;
             stage_windows_2d<Cfg, LC, PITCH, POS>(g, s_rec, s_off, base, npts, win, lane, pow2);
             const float* wv0 = win;
-#if NFFT_REG2_UNROLL
 #pragma unroll
             for (int gp = 0; gp < kReg2Group; ++gp) {
                 if (gp >= npts) break;
-#else
-            for (int gp = 0; gp < npts; ++gp) {
-#endif
                 const float* wv = wv0 + gp * 2 * Cfg::XYP;
                 constexpr int NC2 = (NCOMP + 1) / 2;
                 float2 part2[NC2];
