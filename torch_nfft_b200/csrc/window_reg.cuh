@@ -187,7 +187,7 @@ struct IntC { static constexpr int value = K; };
 // two divisions and three integer modulo operations (ncu source view of the previous flush: 145
 // instructions per quad, 11.7 % of all warp instructions of the spread kernel).
 #ifndef NFFT_REG_WALK_UNROLL
-#define NFFT_REG_WALK_UNROLL 1
+#define NFFT_REG_WALK_UNROLL 4
 #endif
 constexpr int kWalkUnroll = NFFT_REG_WALK_UNROLL;
 template <typename F>
