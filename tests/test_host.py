@@ -131,3 +131,18 @@ def test_graphed_transforms_need_a_gpu():
         pytest.skip("CUDA device present")
     with pytest.raises(RuntimeError):
         T.GraphedTransforms(lambda: None)
+
+
+def test_release_stream_workspace_forgets_only_that_stream():
+    from torch_nfft_b200 import nfft
+    saved = dict(nfft._workspaces), dict(nfft._sorted_points)
+    try:
+        nfft._workspaces[(0, 111)], nfft._workspaces[(0, 222)] = "a", "b"
+        nfft._sorted_points[(0, 111)], nfft._sorted_points[(0, 222)] = "sa", "sb"
+        nfft.release_stream_workspace(0, 111)
+        assert (0, 111) not in nfft._workspaces and (0, 111) not in nfft._sorted_points
+        assert nfft._workspaces[(0, 222)] == "b" and nfft._sorted_points[(0, 222)] == "sb"
+        nfft.release_stream_workspace(0, 333)  # unknown stream: no error
+    finally:
+        nfft._workspaces.clear(); nfft._workspaces.update(saved[0])
+        nfft._sorted_points.clear(); nfft._sorted_points.update(saved[1])

@@ -25,11 +25,13 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .nfft import forget_sorted_points
+from .nfft import forget_sorted_points, release_stream_workspace
 
 
 class GraphedTransforms:
     def __init__(self, fn, warmup: int = 1, device=None):
+        self.graph = None
+        self.outputs = None
         if not torch.cuda.is_available():
             raise RuntimeError("torch_nfft_b200: GraphedTransforms needs a CUDA device")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -55,5 +57,22 @@ class GraphedTransforms:
 
     def replay(self):
         """Runs the captured transforms on the current stream; returns the output tensors of the capture."""
+        if self.graph is None:
+            raise RuntimeError("torch_nfft_b200: this GraphedTransforms has been closed")
         self.graph.replay()
         return self.outputs
+
+    def close(self):
+        """Frees the graph, its outputs and the capture stream's workspace (0.9 GB at BASELINE config c4)."""
+        if getattr(self, "graph", None) is None:
+            return
+        torch.cuda.synchronize(self.device)  # replays still in flight use the workspace
+        self.graph = None
+        self.outputs = None
+        release_stream_workspace(self.device.index, self._stream.cuda_stream)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: modules may already be gone
+            pass

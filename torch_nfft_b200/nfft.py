@@ -53,6 +53,14 @@ def clear_caches():
     _lib.lib().nfftb200_plan_cache_clear()
 
 
+def release_stream_workspace(device_index: int, cuda_stream: int):
+    """Drop the scratch tensor (and remembered sort) kept for one (device, stream): called when the
+    owner of a private stream goes away (`GraphedTransforms.close`)."""
+    key = (device_index, cuda_stream)
+    _workspaces.pop(key, None)
+    _sorted_points.pop(key, None)
+
+
 def forget_sorted_points():
     """Forget which point sets the workspaces hold a sort for (the next transform bins again)."""
     _sorted_points.clear()
