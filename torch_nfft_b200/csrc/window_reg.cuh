@@ -114,6 +114,26 @@ __device__ __forceinline__ float window_exp(float x) {
 #endif
 }
 
+// Shared-memory spin lock of the add-out (lane 0 of the warp).  Experiment switches for the next A/B run
+// (the r01e capture counts 11 CAS attempts per acquisition): NFFT_REG_LOCK_TTAS=1 polls the lock word
+// with a plain volatile load and tries the CAS only when it reads free; NFFT_REG_LOCK_NS is the back-off.
+#ifndef NFFT_REG_LOCK_TTAS
+#define NFFT_REG_LOCK_TTAS 0
+#endif
+#ifndef NFFT_REG_LOCK_NS
+#define NFFT_REG_LOCK_NS 32
+#endif
+__device__ __forceinline__ void lock_acquire(int* lk) {
+#if NFFT_REG_LOCK_TTAS
+    for (;;) {
+        if (*reinterpret_cast<volatile int*>(lk) == 0 && atomicCAS(lk, 0, 1) == 0) break;
+        __nanosleep(NFFT_REG_LOCK_NS);
+    }
+#else
+    while (atomicCAS(lk, 0, 1) != 0) __nanosleep(NFFT_REG_LOCK_NS);
+#endif
+}
+
 // orders the tile updates of a critical section before the lock release (CTA scope).
 // fence.acq_rel is enough; __threadfence_block() is the sequentially consistent fence.sc.cta.
 __device__ __forceinline__ void release_fence() {
@@ -552,7 +572,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     const bool two = 2 * kp + 1 < zlim;
                     int* lk = s_lock + scz * SP + kp;
                     if (lane == 0) {
-                        while (atomicCAS(lk, 0, 1) != 0) __nanosleep(32);
+                        lock_acquire(lk);
                     }
                     __syncwarp();
                     float2 cur[CPL];

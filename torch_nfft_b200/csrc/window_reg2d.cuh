@@ -267,7 +267,7 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
 #pragma unroll
         for (int b = 0; b < kBands; ++b) {
             if (lane == 0) {
-                while (atomicCAS(&s_lock[scy + b], 0, 1) != 0) __nanosleep(32);
+                lock_acquire(&s_lock[scy + b]);
             }
             __syncwarp();
 #pragma unroll
@@ -289,7 +289,7 @@ spread_reg2d_kernel(const Geom g, const WindowArgs a) {
         if (lane == 0) {
 #pragma unroll
             for (int b = 0; b < kBands; ++b)
-                while (atomicCAS(&s_lock[scy + b], 0, 1) != 0) __nanosleep(32);  // ascending order: no deadlock
+                lock_acquire(&s_lock[scy + b]);  // ascending order: no deadlock
         }
         __syncwarp();
 #pragma unroll
