@@ -44,6 +44,40 @@ def save(name, **kw):
 
 
 rng = np.random.default_rng(20240229)
+NEW_ONLY = "--new-only" in sys.argv  # round 2: write only the fixtures added below (the older ones are committed)
+
+# ---- round-2 additions: the instantiations the BASELINE configs run ---------------------------------
+# (own generator, so the round-1 fixtures below stay reproducible bit for bit)
+rng2 = np.random.default_rng(20261018)
+for name, d, N, m, B, n, C, cplx, ro in [
+    ("adjoint_3d_m4_n32", 3, 32, 4, 2, 2500, 1, False, False),      # spread_reg_kernel<10,4,4,2>: the c4 kernel
+    ("adjoint_2d_m4_c8_n64", 2, 64, 4, 2, 3000, 8, False, False),   # spread_reg2d_kernel<10,8>: the c3 kernel
+    ("adjoint_1d_m8_n256", 1, 256, 8, 3, 2000, 1, False, False),    # spread1d_kernel, m = 8: the c2 kernel
+]:
+    pos, batch = points(rng2, n, d, B)
+    x = values(rng2, (n * B, C), cplx)
+    y = ref.nfft_adjoint(t(x), t(pos), t(batch), N, m, ro)
+    y2 = ref.nfft_adjoint(t(x), t(pos), t(batch), N, m, ro)
+    save(name, op="adjoint", pos=pos, batch=batch, x=x, N=N, m=m, real_output=ro, y=y.cpu().numpy(),
+         run_to_run=float((y - y2).abs().max().item()))
+for name, d, N, m, B, n, C, cplx, ro in [
+    ("forward_3d_m4_n32_realout", 3, 32, 4, 2, 2500, 1, True, True),     # gather_reg_kernel<10,4,4,2>
+    ("forward_2d_m4_c8_n64_realout", 2, 64, 4, 2, 3000, 8, True, True),  # gather_reg2d_kernel<10,8>
+    ("forward_1d_m8_n256_realout", 1, 256, 8, 3, 2000, 1, True, True),   # gather1d_kernel, m = 8
+]:
+    pos, batch = points(rng2, n, d, B)
+    xh = values(rng2, (B,) + (N,) * d + (C,), cplx)
+    y = ref.nfft_forward(t(xh), t(pos), t(batch), m, ro)
+    save(name, op="forward", pos=pos, batch=batch, x=xh, m=m, real_output=ro, y=y.cpu().numpy())
+src, sb = points(rng2, 3000, 3, 1, scale=0.5)
+x = values(rng2, (3000, 1), False)
+co = ref.gaussian_interpolated_coeffs(0.1, 3, 32)
+y = ref.nfft_fastsum(t(x), co, t(src), batch=t(sb), cutoff=4)
+save("fastsum_3d_m4_n32_sym_interp", op="fastsum", sources=src, source_batch=sb, x=x, coeffs=co.cpu().numpy(), m=4,
+     y=y.cpu().numpy())
+if NEW_ONLY:
+    print("golden (round-2 additions) done")
+    sys.exit(0)
 
 # ---- adjoint -------------------------------------------------------------------------------
 for name, d, N, m, B, n, C, cplx, ro in [

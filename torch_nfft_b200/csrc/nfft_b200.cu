@@ -316,15 +316,16 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         return NFFTB200_OK;
     }
     if (g.use_reg == 1) {
-        // supercell 4 x 4 x 2 cells; for m = 4 the register block is 13 x 13 x 12: 6 positions x 6
-        // float2 accumulators per lane
+        // supercell kRegSX x kRegSY x kRegSZ = 4 x 4 x 2 cells; for m = 4 the register block is 13 x 13 x 12:
+        // 6 positions x 6 float2 accumulators per lane
         WindowKernel kern = nullptr;
         int win_floats = 0;
         switch (g.m) {
 #define NF_REG_CASE(M_, L_)                                                                          \
             case M_:                                                                                 \
-                kern = spread ? spread_reg_kernel<L_, 4, 4, 2> : gather_reg_kernel<L_, 4, 4, 2>;     \
-                win_floats = RegCfg<L_, 4, 4, 2>::WIN_FLOATS;                                        \
+                kern = spread ? spread_reg_kernel<L_, kRegSX, kRegSY, kRegSZ>                        \
+                              : gather_reg_kernel<L_, kRegSX, kRegSY, kRegSZ>;                       \
+                win_floats = RegCfg<L_, kRegSX, kRegSY, kRegSZ>::WIN_FLOATS;                         \
                 break;
             NF_REG_CASE(1, 4)
             NF_REG_CASE(2, 6)
@@ -333,7 +334,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
 #undef NF_REG_CASE
             default: NF_FAIL(NFFTB200_ERR_INVALID, "register-stencil kernels need m <= 4");
         }
-        const int nsc = ((g.T[0] + 3) / 4) * ((g.T[1] + 3) / 4) * ((g.T[2] + 1) / 2);
+        const int nsc = ((g.T[0] + kRegSX - 1) / kRegSX) * ((g.T[1] + kRegSY - 1) / kRegSY) * ((g.T[2] + kRegSZ - 1) / kRegSZ);
         const size_t smem = reg_smem_bytes(g, nsc, win_floats);
         if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
         NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -33,6 +33,18 @@ constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) hel
 #ifndef NFFT_REG_FFMA2
 #define NFFT_REG_FFMA2 1
 #endif
+// supercell of the 3D sweep (oversampled cells along X, Y, Z); 2 bits per offset in s_off
+#ifndef NFFT_REG_SX
+#define NFFT_REG_SX 4
+#endif
+#ifndef NFFT_REG_SY
+#define NFFT_REG_SY 4
+#endif
+#ifndef NFFT_REG_SZ
+#define NFFT_REG_SZ 2
+#endif
+constexpr int kRegSX = NFFT_REG_SX, kRegSY = NFFT_REG_SY, kRegSZ = NFFT_REG_SZ;
+static_assert(kRegSX <= 4 && kRegSY <= 4 && kRegSZ <= 4, "cell offsets inside a supercell are stored in 2 bits");
 constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round: one lane per (point, dimension), 3 * 8 <= 32
 static_assert(kRegGroup == 8, "the sweeps have one point body per slot of an 8-point round");
 constexpr int kGatherSlots = 8;  // point slots of a gather round (= kRegGroup)
