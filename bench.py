@@ -12,9 +12,20 @@ quoted on.  For N > 1 every rank transforms its own 4 batch entries (batch shard
 data-path collective): weak scaling.
 
 Printed JSON (rank 0, one line): see the keys below.  `value` has inputs resident in HBM;
-`e2e` goes through the public API with pinned HOST buffers (H2D of pos/x/batch and D2H of both
-results inside the timed region).  `roofline` is for the dominant kernel (spread), from CUDA
+`e2e` goes through the public API with pinned HOST buffers (H2D of pos / x / batch offsets and D2H of
+both results inside the timed region).  `roofline` is for the dominant kernel (spread), from CUDA
 events recorded inside the library around that stage during the timed region.
+
+Every step bins its points once (`NfftPlan`, made inside the step) and uses that binning for the
+adjoint and the forward transform of the pair; nothing is carried from one step to the next.  The
+point sets are described by batch_size + 1 offsets (`batch_ptr`) instead of the reference's per-point
+int64 vector, which the engine accepts too.
+
+Extra objects in the same line: `extra_workloads` (N = 1: c4 Gaussian-clustered, c3, c2 eager and as a
+CUDA graph), and for --gpus N > 1 `strong_c4` (the SAME 2^24-point c4 spread over the N GPUs: batch
+entries first, then a 2-way point split per entry with a pairwise all-reduce of the 67 MB grid) and
+`c5_point_sharded` (BASELINE config c5: 2^26-point 3D fastsum, points split over the N GPUs, one
+all-reduce of the 8 MB grid per product), each with its own CUDA-event time and the collective's.
 """
 import argparse
 import json
@@ -66,6 +77,11 @@ def make_inputs(torch, workload, device, seed):
     x = torch.randn(n, C, device=device, generator=gen)
     batch = torch.arange(n, device=device) // (n // B)
     return pos.contiguous(), x.contiguous(), batch.contiguous()
+
+
+def batch_offsets(torch, n, B, device):
+    """batch_size + 1 int64 offsets of the point sets (n / B points each, like make_inputs' batch vector)."""
+    return (torch.arange(B + 1, dtype=torch.int64) * (n // B)).to(device)
 
 
 class ClockSampler:
@@ -203,6 +219,145 @@ def bind_to_gpu_numa_node(torch, local):
     return None
 
 
+def time_pairs(torch, T, workload, dev, steps, warmup=3, seed=99, graph=False):
+    """Device-timed adjoint+forward pairs of another BASELINE workload (inputs resident, one binning per step):
+    the `extra_workloads` entries of the default line."""
+    d, N, m, n, B, C, distribution = WORKLOADS[workload]
+    pos, x, _ = make_inputs(torch, workload, dev, seed=seed)
+    ptr = batch_offsets(torch, n, B, dev)
+
+    def step():
+        plan = T.NfftPlan(pos, batch_ptr=ptr)
+        y = T.nfft_adjoint(x, plan=plan, N=N, m=m)
+        return T.nfft_forward(y, plan=plan, m=m, real_output=True)
+
+    def run(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms = run(step)
+    alg = algorithmic_bytes(d, N, n, B, C)
+    peak, _ = measured_peak_gbs()
+    out = {"workload": f"{d}D N={N} m={m} n={n} {distribution} B={B} C={C}", "ms_per_step": ms,
+           "value": n / (ms * 1e-3), "unit": "points/s", "steps": steps,
+           "whole_step_hbm_frac": (alg["adjoint"] + alg["forward"]) / (ms * 1e-3) / 1e9 / peak}
+    if graph:
+        graphed = T.GraphedTransforms(step)
+        ms_g = run(graphed.replay)
+        out["cuda_graph"] = {"ms_per_step": ms_g, "value": n / (ms_g * 1e-3), "kernels_per_replay": int(graphed.kernels_per_replay)}
+        graphed.close()
+    del pos, x, ptr
+    torch.cuda.empty_cache()
+    return out
+
+
+def timed_max(torch, dist, dev, fn, steps, warmup, world):
+    """K steps bracketed by barrier + synchronize, CUDA events, maximum over the ranks (ms per step)."""
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def strong_c4(torch, dist, T, D, dev, rank, world, steps):
+    """The SAME 2^24-point c4 (B = 4 point sets of 2^22) spread over the ranks: whole point sets per rank while
+    world <= 4 (no collective); for world = 8 every point set is split over a PAIR of ranks, each spreading its
+    half into a partial 256^3 grid, summed by a pairwise all-reduce of the 67 MB grid."""
+    d, N, m, n, B, C, _ = WORKLOADS["c4"]
+    if world not in (1, 2, 4, 8):
+        return None
+    per_set = n // B
+    split = max(1, world // B)                      # ranks per point set
+    sets_here = max(1, B // world)                  # point sets per rank
+    group = None
+    if split > 1:
+        groups = [dist.new_group(list(range(g * split, (g + 1) * split))) for g in range(world // split)]
+        group = groups[rank // split]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    n_here = per_set * sets_here // split
+    pos = torch.rand(n_here, d, device=dev, generator=gen) - 0.5
+    x = torch.randn(n_here, C, device=dev, generator=gen)
+    if split == 1:
+        ptr = batch_offsets(torch, n_here, sets_here, dev)
+
+        def step():
+            plan = T.NfftPlan(pos, batch_ptr=ptr)
+            y = T.nfft_adjoint(x, plan=plan, N=N, m=m)
+            return T.nfft_forward(y, plan=plan, m=m, real_output=True)
+    else:
+        def step():
+            y = D.nfft_adjoint_point_sharded(x, pos, None, N, m, batch_size=1, group=group)
+            return D.nfft_forward_point_sharded(y, pos, None, m, True, batch_size=1, group=group)
+    ms = timed_max(torch, dist, dev, step, steps, 3, world)
+    out = {"workload": "c4: 3D N=128 m=4, 2^24 uniform points in 4 point sets, adjoint+forward", "nranks": world,
+           "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "points/s", "scaling": "strong",
+           "sharding": f"{sets_here} point set(s) per rank" if split == 1 else
+                       f"each point set split over {split} ranks (point sharding)",
+           "collective": None}
+    if split > 1:
+        buf = torch.zeros((2 * N) ** d, device=dev)
+
+        def coll():
+            dist.all_reduce(buf, group=group)
+        cms = timed_max(torch, dist, dev, coll, 10, 3, world)
+        out["collective"] = {"op": f"all_reduce(sum) of the partial real grid within each group of {split} ranks (NCCL)",
+                             "bytes": buf.numel() * 4, "ms": cms, "per_step": 1}
+    return out
+
+
+def c5_point_sharded(torch, dist, T, D, dev, rank, world, steps):
+    """BASELINE config c5: 3D fastsum with a Gaussian kernel, N=64, m=4, 2^26 points (max-norm 1/4) split over
+    the ranks; every rank spreads its slice, ONE all-reduce sums the 128^3 grids, the spectral stage runs on
+    every rank, every rank gathers at its own points."""
+    n_total, N, m = 2 ** 26, 64, 4
+    n = n_total // world
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(100 + rank)
+    pos = (torch.rand(n, 3, device=dev, generator=gen) - 0.5) * 0.5
+    x = torch.randn(n, 1, device=dev, generator=gen)
+    coeffs = T.gaussian_interpolated_coeffs(0.1, 3, N)
+
+    def step():
+        return D.nfft_fastsum_point_sharded(x, coeffs, pos, cutoff=m, batch_size=1)
+    ms = timed_max(torch, dist, dev, step, steps, 2, world)
+    out = {"workload": "c5: 3D fastsum (Gaussian kernel, sigma 0.1), N=64 m=4, 2^26 points in [-1/4,1/4]^3, symmetric",
+           "nranks": world, "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "points/s", "scaling": "strong",
+           "sharding": "points split evenly over the ranks", "collective": None}
+    if world > 1:
+        buf = torch.zeros((2 * N) ** 3, device=dev)
+
+        def coll():
+            dist.all_reduce(buf)
+        cms = timed_max(torch, dist, dev, coll, 10, 3, world)
+        out["collective"] = {"op": "all_reduce(sum) of the partial 128^3 real grid over all ranks (NCCL)",
+                             "bytes": buf.numel() * 4, "ms": cms, "per_step": 1}
+    del pos, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -220,24 +375,29 @@ def run_ours(args):
     d, N, m, n, B, C, distribution = WORKLOADS[args.workload]
 
     pos, x, batch = make_inputs(torch, args.workload, dev, seed=1234 + rank)
+    del batch                                     # the point sets are described by B + 1 offsets
+    ptr = batch_offsets(torch, n, B, dev)
     # pinned host copies for the end-to-end arm
-    h_pos, h_x, h_batch = (t.cpu().pin_memory() for t in (pos, x, batch))
+    h_pos, h_x, h_ptr = (t.cpu().pin_memory() for t in (pos, x, ptr))
     h_spec = torch.empty((B,) + (N,) * d + (C,), dtype=torch.complex64).pin_memory()
     h_y = torch.empty((n, C), dtype=torch.float32).pin_memory()
 
+    def pair(x_, pos_, ptr_):
+        # every step is a fresh transform pair: its points are binned once (NfftPlan) and the adjoint and the
+        # forward transform of the pair share that binning, as forward + backward of autograd do
+        plan = T.NfftPlan(pos_, batch_ptr=ptr_)
+        y = T.nfft_adjoint(x_, plan=plan, N=N, m=m)
+        return y, T.nfft_forward(y, plan=plan, m=m, real_output=True)
+
     def step_device():
-        # every step is a fresh transform pair: the points are binned again (the adjoint sorts, the
-        # forward of the same pair reuses that sort, as forward + backward of autograd would)
-        T.forget_sorted_points()
-        y = T.nfft_adjoint(x, pos, batch, N, m, batch_size=B)
-        return T.nfft_forward(y, pos, batch, m, real_output=True, batch_size=B)
+        return pair(x, pos, ptr)[1]
 
     # End-to-end arm: every step copies ITS inputs from pinned host memory and reads ITS results back.
     # Like a data loader, the copies of step k+1 (copy stream) overlap the transforms of step k
     # (compute stream) through two device buffer sets; results leave on a third stream.
     compute_stream = torch.cuda.current_stream(dev)
     h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    dbuf = [(torch.empty_like(pos), torch.empty_like(x), torch.empty_like(batch)) for _ in range(2)]
+    dbuf = [(torch.empty_like(pos), torch.empty_like(x), torch.empty_like(ptr)) for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]   # inputs of the buffer set have arrived
     ev_free = [torch.cuda.Event() for _ in range(2)]    # the transforms reading the buffer set are done
     e2e_state = {"k": 0, "staged": False, "keep": None}
@@ -245,10 +405,10 @@ def run_ours(args):
     def stage_inputs(slot):
         with torch.cuda.stream(h2d_stream):
             h2d_stream.wait_event(ev_free[slot])
-            dpos, dx, dbatch = dbuf[slot]
+            dpos, dx, dptr = dbuf[slot]
             dpos.copy_(h_pos, non_blocking=True)
             dx.copy_(h_x, non_blocking=True)
-            dbatch.copy_(h_batch, non_blocking=True)
+            dptr.copy_(h_ptr, non_blocking=True)
             ev_ready[slot].record(h2d_stream)
 
     def step_e2e():
@@ -259,9 +419,8 @@ def run_ours(args):
         stage_inputs(1 - slot)                 # inputs of the NEXT step travel while this one computes
         e2e_state["staged"] = True
         compute_stream.wait_event(ev_ready[slot])
-        dpos, dx, dbatch = dbuf[slot]
-        y = T.nfft_adjoint(dx, dpos, dbatch, N, m, batch_size=B)
-        f = T.nfft_forward(y, dpos, dbatch, m, real_output=True, batch_size=B)
+        dpos, dx, dptr = dbuf[slot]
+        y, f = pair(dx, dpos, dptr)
         ev_free[slot].record(compute_stream)
         done = torch.cuda.Event()
         done.record(compute_stream)
@@ -355,6 +514,26 @@ def run_ours(args):
         e2e_state["k"] = 2
         ms_e2e, _, _ = timed_e2e(step_e2e, finish_e2e, args.steps)
 
+    # the other BASELINE configurations (device-timed, inputs resident), rank 0 at N = 1 only
+    extra = None
+    multi = {}
+    if not args.no_extras:
+        del dbuf
+        torch.cuda.empty_cache()
+        if world == 1 and args.workload == "c4":
+            ks = max(3, min(args.steps, 10))
+            extra = {"c4_clustered": time_pairs(torch, T, "c4_clustered", dev, ks),
+                     "c3": time_pairs(torch, T, "c3", dev, ks),
+                     "c2": time_pairs(torch, T, "c2", dev, 50, warmup=5, graph=True)}
+        if args.workload == "c4":
+            from torch_nfft_b200 import dist as D
+            ks = max(3, min(args.steps, 10))
+            if world > 1:
+                del pos, x
+                torch.cuda.empty_cache()
+                multi["strong_c4"] = strong_c4(torch, dist, T, D, dev, rank, world, ks)
+            multi["c5_point_sharded"] = c5_point_sharded(torch, dist, T, D, dev, rank, world, max(3, min(args.steps, 5)))
+
     if rank == 0:
         ms_step = ms_total / args.steps
         alg = algorithmic_bytes(d, N, n, B, C)
@@ -379,11 +558,14 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {d}D adjoint+forward NFFT, N={N}, m={m}, n={n} {distribution} "
                                    f"points per GPU, batch_size={B}, {C} channel(s), real x -> complex spectrum -> real y",
                        "sharding": "batch entries per GPU, no collective" if world > 1 else "single GPU",
-                       "sort_reuse": "within a step only (adjoint -> forward of the same points); re-sorted every step",
-                       "l2": "inputs larger than L2 (pos+x+batch = %d MB per step, grid %d MB)" % (
-                           (n * (4 * d + 4 * C + 8)) >> 20, (B * C * (2 * N) ** d * 4) >> 20)},
+                       "binning": "once per step (NfftPlan made inside the step, shared by its adjoint and forward); "
+                                  "nothing is reused across steps",
+                       "point_sets": "batch_ptr: batch_size + 1 int64 offsets (the per-point int64 batch vector of the "
+                                     "reference is accepted too)",
+                       "l2": "inputs larger than L2 (pos+x = %d MB per step, grid %d MB)" % (
+                           (n * (4 * d + 4 * C)) >> 20, (B * C * (2 * N) ** d * 4) >> 20)},
             "e2e": {"value": n * world / (ms_e2e / args.steps * 1e-3), "unit": "points/s",
-                    "h2d_bytes_per_step": n * (4 * d + 4 * C + 8),
+                    "h2d_bytes_per_step": n * (4 * d + 4 * C) + 8 * (B + 1),
                     "d2h_bytes_per_step": B * C * N ** d * 8 + n * C * 4,
                     "host_numa_node_rank0": numa},
             "gpu_launches": int(launches),
@@ -403,6 +585,9 @@ def run_ours(args):
         }
         if graph_info is not None:
             out["cuda_graph"] = graph_info
+        if extra is not None:
+            out["extra_workloads"] = extra
+        out.update(multi)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -441,17 +626,17 @@ def run_reference(args):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     pos, x, batch = make_inputs(torch, args.workload, dev, seed=1234)
-    # Bounded sample: the reference needs ~23 s per adjoint+forward pair at the full 2^24 points (one
-    # global atomic per tap), so a step transforms every `stride`-th point of each point set: same grid
-    # (N, m, batch_size, channels), n / stride points.  Its cost is linear in n (fixed costs: < 1 %).
+    # The reference needs ~23 s per adjoint+forward pair at the full 2^24 points (one global atomic per tap).
+    # The arm runs the FULL workload (same_config) whenever steps + warm-up fit a ~12 minute run -- the driver's
+    # `--steps 20 --warmup 5` does (25 x 24 s = 10 min).  Only longer requests fall back to a bounded sample
+    # (every `stride`-th point of each point set: same grid, n / stride points; its cost is linear in n).
+    budget_s = 720.0
     if args.ref_points > 0:
         ref_points = args.ref_points
     else:
-        # auto: the largest power-of-two share of the workload that keeps the whole run near 4 minutes
-        # (measured on B200: about 0.85 s fixed + 1.3 us per point per adjoint+forward pair)
-        per_step = 240.0 / max(args.steps + max(args.warmup, 1), 1)
+        # measured on B200: about 0.85 s fixed + 1.38 us per point per adjoint+forward pair
         ref_points = n
-        while ref_points > 2 ** 18 and 0.85 + 1.31e-6 * ref_points > per_step:
+        while ref_points > 2 ** 18 and (0.85 + 1.38e-6 * ref_points) * (args.steps + max(args.warmup, 1)) > budget_s:
             ref_points //= 2
     stride = max(1, n // ref_points)
     if stride > 1:
@@ -477,8 +662,9 @@ def run_reference(args):
                  "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "config": dict(base["config"], arm="reference CUDA NFFT (baseline/_ref, torch_nfft.nfft_adjoint + "
                                                     "nfft_forward), inputs resident on the GPU",
-                                sample=f"{ns} of the {n} points per step (every {stride}-th point of each point set), "
-                                       f"full grid N={N}, batch_size={B}")})
+                                sample=("the full workload" if stride == 1 else
+                                        f"{ns} of the {n} points per step (every {stride}-th point of each point set)")
+                                       + f", full grid N={N}, batch_size={B}", same_config=stride == 1)})
     print(json.dumps(base))
 
 

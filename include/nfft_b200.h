@@ -50,21 +50,29 @@ extern "C" {
 #define NFFTB200_OP_GATHER 4
 #define NFFTB200_OP_SORT 5
 #define NFFTB200_OP_SPECTRAL 6 /* adjoint_finish / forward_begin / fastsum_middle */
+#define NFFTB200_OP_PLAN 7     /* nfftb200_plan_points (sort scratch only)            */
 
 /* flags */
 #define NFFTB200_X_COMPLEX 1      /* input values are complex64                              */
 #define NFFTB200_Y_REAL 2         /* adjoint/forward: write only the real part (real_output) */
 #define NFFTB200_COEFFS_COMPLEX 4 /* fastsum: coeffs are complex64                           */
 #define NFFTB200_SYMMETRIC 8      /* fastsum: targets are the sources (reuse the sort)       */
-#define NFFTB200_PRESORTED 16     /* adjoint/forward: the workspace still holds the sort of  */
-                                  /* exactly these points (same pos, batch, d, N, m, B, C    */
-                                  /* and value type) from the previous call on it            */
+#define NFFTB200_PLANNED 16       /* *_planned / spread / gather: the caller passes the point */
+                                  /* plan(s) made by nfftb200_plan_points for exactly these   */
+                                  /* points and this geometry; the workspace then holds no    */
+                                  /* sort regions (also a flag of nfftb200_workspace_bytes)   */
+#define NFFTB200_BATCH_OFFSETS 32 /* the `batch` pointers are B+1 ascending int64 OFFSETS of  */
+                                  /* the point sets (CSR style) instead of one entry per point */
 
 int nfftb200_version(void);
 const char* nfftb200_last_error(void);
 
 /* Bytes of device workspace the given call needs (0 on invalid arguments).
- * n_src / n_tgt: number of points spread / gathered (adjoint: n_src, forward: n_tgt). */
+ * n_src / n_tgt: number of points spread / gathered (adjoint: n_src, forward: n_tgt).
+ * The workspace is [sort scratch | point plan(s) | grid | half spectrum | cuFFT work area]: cuFFT plans are
+ * cached per (device, shape) WITHOUT a work area of their own; it is taken from the caller's workspace on
+ * every call, so concurrent streams and captured CUDA graphs never share FFT scratch.  (Without a usable
+ * device the work-area term is 0; the figure is then a lower bound.) */
 size_t nfftb200_workspace_bytes(int op, int64_t n_src, int64_t n_tgt, int d, int64_t N, int m,
                                 int64_t B, int64_t C, int flags);
 
@@ -88,15 +96,49 @@ int nfftb200_fastsum(const float* sources, const float* targets, const void* x, 
                      int64_t n_src, int64_t n_tgt, int d, int64_t N, int m, int64_t B, int64_t C,
                      int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- point plans -------------------------------------------------------------------------
+ * The binning of a point set (stable permutation by grid tile, bin offsets, work items) can be made once
+ * and reused by every transform of the same points with the same tiling -- adjoint -> forward, forward ->
+ * backward, iterative solvers -- where the reference recomputes its per-point scratch in every call
+ * (core_cuda.cu:188-211, 461-484).  The plan lives in a caller-owned device buffer of nfftb200_plan_bytes
+ * (about 4 bytes per point).  n_geom: the point count the TILING is chosen for (0 or n for adjoint / forward;
+ * max(n_src, n_tgt) for both plans of a fastsum).  A plan is valid for one (d, N, m, B, C, real/complex
+ * values) geometry and the positions it was made from; transforms count the points they find outside their
+ * tile in the plan's flag word (nfftb200_plan_flags) instead of writing out of bounds. */
+size_t nfftb200_plan_bytes(int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B, int64_t C,
+                           int flags);
+int nfftb200_plan_points(const float* pos, const int64_t* batch, void* plan, size_t plan_bytes,
+                         int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B, int64_t C,
+                         int flags, void* workspace, size_t workspace_bytes, void* stream);
+/* flags_out[8] on the HOST; flags_out[0] = points found outside their tile so far.  Synchronises. */
+int nfftb200_plan_flags(const void* plan, int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B,
+                        int64_t C, int flags, uint32_t* flags_out, void* stream);
+
+/* The three operators with caller-kept plans (flags must contain NFFTB200_PLANNED; `batch` is unused then
+ * and may be NULL).  Without NFFTB200_PLANNED they bin the points into the workspace like the plain calls. */
+int nfftb200_adjoint_planned(const float* pos, const void* x, const int64_t* batch, const void* plan,
+                             size_t plan_bytes, void* y, int64_t n, int d, int64_t N, int m, int64_t B,
+                             int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream);
+int nfftb200_forward_planned(const float* pos, const void* xhat, const int64_t* batch, const void* plan,
+                             size_t plan_bytes, void* y, int64_t n, int d, int64_t N, int m, int64_t B,
+                             int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream);
+int nfftb200_fastsum_planned(const float* sources, const float* targets, const void* x, const void* coeffs,
+                             const int64_t* source_batch, const int64_t* target_batch,
+                             const void* source_plan, size_t source_plan_bytes, const void* target_plan,
+                             size_t target_plan_bytes, void* y, int64_t n_src, int64_t n_tgt, int d,
+                             int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* ---- split entry points (multi-GPU point sharding, tests) --------------------------------
  * grid: oversampled grid, planar per (b,c): float32 [B*C, M^d] for real values, complex64
  * [B*C, M^d] with NFFTB200_X_COMPLEX.  M = 2N.  */
 
 /* adjoint stage 1 (compute_shifts/compute_psi/adjoint_window_convolution kernels,
- * spatial_window_operations.cu:38-211): grid = sum of window contributions (grid is zeroed). */
-int nfftb200_spread(const float* pos, const void* x, const int64_t* batch, void* grid, int64_t n,
-                    int d, int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace,
-                    size_t workspace_bytes, void* stream);
+ * spatial_window_operations.cu:38-211): grid = sum of window contributions (grid is zeroed).
+ * plan / plan_bytes: a kept point plan with NFFTB200_PLANNED, else NULL / 0. */
+int nfftb200_spread(const float* pos, const void* x, const int64_t* batch, const void* plan,
+                    size_t plan_bytes, void* grid, int64_t n, int d, int64_t N, int m, int64_t B,
+                    int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* adjoint stage 2 (cuFFT + adjoint_rolloff_correction, core_cuda.cu:254-326): grid -> y.
  * The grid is consumed (may be overwritten). */
@@ -111,9 +153,9 @@ int nfftb200_forward_begin(const void* xhat, void* grid, int d, int64_t N, int m
 
 /* forward stage 2 (forward_window_convolution, spatial_window_operations.cu:214-332):
  * y[i,c] = sum of window-weighted grid values.  NFFTB200_X_COMPLEX: grid and y complex64. */
-int nfftb200_gather(const float* pos, const int64_t* batch, const void* grid, void* y, int64_t n,
-                    int d, int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace,
-                    size_t workspace_bytes, void* stream);
+int nfftb200_gather(const float* pos, const int64_t* batch, const void* plan, size_t plan_bytes,
+                    const void* grid, void* y, int64_t n, int d, int64_t N, int m, int64_t B, int64_t C,
+                    int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* fastsum middle stage (FFT, kernel_convolution, FFT; core_cuda.cu:683-765): grid -> grid. */
 int nfftb200_fastsum_middle(void* grid, const void* coeffs, int d, int64_t N, int m, int64_t B,
@@ -138,8 +180,16 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
 void nfftb200_profile_enable(int on);
 int nfftb200_profile_read(double* ms_out, int64_t* count_out);
 
-/* Destroys cached cuFFT plans (all devices). */
+/* Tests: force the 64-bit index variants of the spectral kernels (normally chosen when B*C*M^d >= 2^31). */
+void nfftb200_debug_force_int64(int on);
+
+/* cuFFT plan cache: an LRU of handles per (device, dimension, M, type, B*C).  _clear destroys them (all
+ * devices) and fails with NFFTB200_ERR_INVALID while the cache is pinned; _pin(+1/-1) is called by owners of
+ * captured CUDA graphs, whose FFT kernels reference the handles' twiddle tables, and returns the pin count;
+ * _size returns the number of cached handles. */
 int nfftb200_plan_cache_clear(void);
+int nfftb200_plan_cache_pin(int delta);
+int nfftb200_plan_cache_size(void);
 
 /* Number of kernels this library launched so far in this process (for bench.py). */
 int64_t nfftb200_launch_count(void);

@@ -135,14 +135,48 @@ def test_graphed_transforms_need_a_gpu():
 
 def test_release_stream_workspace_forgets_only_that_stream():
     from torch_nfft_b200 import nfft
-    saved = dict(nfft._workspaces), dict(nfft._sorted_points)
+    saved = dict(nfft._workspaces)
     try:
         nfft._workspaces[(0, 111)], nfft._workspaces[(0, 222)] = "a", "b"
-        nfft._sorted_points[(0, 111)], nfft._sorted_points[(0, 222)] = "sa", "sb"
         nfft.release_stream_workspace(0, 111)
-        assert (0, 111) not in nfft._workspaces and (0, 111) not in nfft._sorted_points
-        assert nfft._workspaces[(0, 222)] == "b" and nfft._sorted_points[(0, 222)] == "sb"
+        assert (0, 111) not in nfft._workspaces
+        assert nfft._workspaces[(0, 222)] == "b"
         nfft.release_stream_workspace(0, 333)  # unknown stream: no error
     finally:
-        nfft._workspaces.clear(); nfft._workspaces.update(saved[0])
-        nfft._sorted_points.clear(); nfft._sorted_points.update(saved[1])
+        nfft._workspaces.clear(); nfft._workspaces.update(saved)
+
+
+def test_plan_and_batch_ptr_argument_checks_need_no_gpu():
+    """NfftPlan / batch_ptr validate like check_point_input (core_cuda.cu:38-66): CPU tensors raise."""
+    pos = torch.rand(10, 2) - 0.5
+    with pytest.raises(RuntimeError):
+        T.NfftPlan(pos)
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(torch.rand(10), pos, batch_ptr=torch.tensor([0, 10]))
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(torch.rand(10))  # neither pos nor plan
+
+
+def test_plan_cache_pin_blocks_clear():
+    """Captured CUDA graphs pin the cuFFT handle cache (their kernels reference the handles' twiddle
+    tables): clearing is refused with a message until the pin is released.  Host-only bookkeeping."""
+    from torch_nfft_b200 import _lib
+    L = _lib.lib()
+    assert L.nfftb200_plan_cache_clear() == 0
+    assert L.nfftb200_plan_cache_pin(1) == 1
+    try:
+        assert L.nfftb200_plan_cache_clear() != 0 and b"pinned" in L.nfftb200_last_error()
+        with pytest.warns(RuntimeWarning):
+            T.clear_caches()
+    finally:
+        assert L.nfftb200_plan_cache_pin(-1) == 0
+    assert L.nfftb200_plan_cache_clear() == 0
+
+
+def test_point_limits_are_rejected():
+    """n is int64 across the ABI but permutation / bin offsets are 32-bit: oversize inputs are refused."""
+    from torch_nfft_b200 import _lib
+    L = _lib.lib()
+    assert L.nfftb200_workspace_bytes(_lib.OP_ADJOINT, 2 ** 32, 0, 3, 128, 4, 4, 1, 0) == 0
+    assert b"points" in L.nfftb200_last_error()
+    assert L.nfftb200_plan_bytes(2 ** 33, 0, 1, 1024, 8, 1, 1, 0) == 0

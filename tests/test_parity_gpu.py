@@ -371,49 +371,158 @@ def test_full_size_properties(name, clustered):
 
 
 # ---------------------------------------------------------------------------------------------
-# reuse of the point sort between transforms of the same point set
+# point plans: the binning of a point set is made once and reused
 # ---------------------------------------------------------------------------------------------
-def test_sort_reuse_between_adjoint_and_forward():
-    from torch_nfft_b200 import nfft as nfft_mod
+BINNING_LAUNCHES = 5  # the binning alone is at least this many kernels (keys, scans, scatter, items)
+
+
+def test_plan_reuses_the_binning_between_transforms():
     rng = np.random.default_rng(11)
     pos, batch = make_points(rng, 3, 2, 3000)
     x = make_values(rng, (pos.shape[0], 1), False)
     tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
     T.clear_caches()
+    ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
+    ref_f = O.nfft_forward(ref_y, pos, batch, 4, real_output=True)
+    # without a plan every transform bins the points
     before = _lib.launch_count()
-    y = T.nfft_adjoint(tx, tp, tb, 32, 4)
+    y0 = T.nfft_adjoint(tx, tp, tb, 32, 4)
+    unplanned = _lib.launch_count() - before
+    # with a plan: the first transform bins, the following ones do not
+    plan = T.NfftPlan(tp, tb)
+    before = _lib.launch_count()
+    y = T.nfft_adjoint(tx, plan=plan, N=32, m=4)
     first = _lib.launch_count() - before
-    f = T.nfft_forward(y, tp, tb, 4, real_output=True)  # same points, same tiling: no second sort
+    f = T.nfft_forward(y, plan=plan, m=4, real_output=True)  # same points, same tiling: no second binning
     second = _lib.launch_count() - before - first
-    assert second <= 4 and first - second >= 5, (first, second)  # the binning alone is >= 5 launches
-    ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
-    assert O.rel_l2(y.cpu().numpy(), ref_y) < TOL
-    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, 4, real_output=True)) < TOL
-    # an in-place change of the points invalidates the remembered sort
-    tp.mul_(0.5)
-    f2 = T.nfft_forward(y, tp, tb, 4, real_output=True)
-    assert O.rel_l2(f2.cpu().numpy(), O.nfft_forward(ref_y, (pos * 0.5).astype(np.float32), batch, 4, real_output=True)) < TOL
-    # a different tensor with the same shape is never taken for the remembered one
-    tp2 = cuda(pos)
-    f3 = T.nfft_forward(y, tp2, tb, 4, real_output=True)
-    assert O.rel_l2(f3.cpu().numpy(), f.cpu().numpy()) < 1e-6
-    assert nfft_mod._PLAN_REUSE
+    y2 = T.nfft_adjoint(tx, tp, tb, 32, 4, plan=plan)        # pos / batch may be passed along with their plan
+    third = _lib.launch_count() - before - first - second
+    assert first >= unplanned and second <= 4 and third <= 4 and first - third >= BINNING_LAUNCHES, (unplanned, first, second, third)
+    assert plan.sorts == 1 and 4 * pos.shape[0] <= plan.nbytes < 8 * pos.shape[0] + (1 << 20)
+    assert O.rel_l2(y0.cpu().numpy(), ref_y) < TOL and O.rel_l2(y.cpu().numpy(), ref_y) < TOL
+    assert O.rel_l2(y2.cpu().numpy(), ref_y) < TOL and O.rel_l2(f.cpu().numpy(), ref_f) < TOL
+    assert plan.dropped_points() == 0
+    # a plan refuses other tensors
+    with pytest.raises(RuntimeError):
+        T.nfft_adjoint(tx, cuda(pos), tb, 32, 4, plan=plan)
 
 
-def test_sort_reuse_is_invalidated_by_other_users_of_the_workspace():
-    """Split-stage calls (dist engine) and fastsum share the workspace: a remembered sort must not
-    survive them."""
-    from torch_nfft_b200 import dist as D
+def test_stale_plan_is_detected_and_never_writes_out_of_bounds():
+    """The caller owns a plan's validity.  If the positions change behind its back (a write through
+    `.data`, another CUDA graph, a custom kernel: nothing the engine can see), the transforms drop the points
+    they find outside their tile and count them instead of indexing shared memory out of bounds."""
     rng = np.random.default_rng(12)
-    pos, batch = make_points(rng, 3, 2, 4000)
-    x = make_values(rng, (pos.shape[0], 1), False)
-    tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
-    y = T.nfft_adjoint(tx, tp, tb, 32, 4)                      # remembers the sort of tp
-    half = pos.shape[0] // 2
-    D.CudaEngine().spread(tx[:half], tp[:half], tb[:half], 2, 32, 4)  # overwrites the sort region
-    f = T.nfft_forward(y, tp, tb, 4, real_output=True)          # must sort again
-    ref_y = O.nfft_adjoint(x, pos, batch, 32, 4)
-    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, 4, real_output=True)) < TOL
+    for d, N, m in [(3, 32, 4), (2, 32, 4), (1, 256, 8), (3, 32, 6), (2, 32, 2)]:  # reg 3D / reg 2D / 1D / team 3D / team 2D
+        pos, batch = make_points(rng, d, 2, 3000)
+        x = make_values(rng, (pos.shape[0], 1), False)
+        tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
+        plan = T.NfftPlan(tp, tb)
+        y = T.nfft_adjoint(tx, plan=plan, N=N, m=m)
+        assert plan.dropped_points() == 0
+        assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(x, pos, batch, N, m)) < TOL
+        tp.data.copy_(cuda(rng.random(pos.shape, dtype=np.float32) - 0.5))  # new positions, same tensor
+        T.nfft_adjoint(tx, plan=plan, N=N, m=m)
+        T.nfft_forward(y, plan=plan, m=m)
+        torch.cuda.synchronize()
+        assert plan.dropped_points() > 0, (d, N, m)
+        # a fresh plan of the new positions is exact again
+        fresh = T.NfftPlan(tp, tb)
+        y2 = T.nfft_adjoint(tx, plan=fresh, N=N, m=m)
+        assert O.rel_l2(y2.cpu().numpy(), O.nfft_adjoint(x, tp.cpu().numpy(), batch, N, m)) < TOL
+        assert fresh.dropped_points() == 0
+
+
+def test_gram_matrix_bins_its_points_once():
+    """`A @ x` of the kernel-matrix layer: the first product bins sources and targets, products 2..k launch
+    no binning kernel (the reference recomputes its per-point scratch every time, core_cuda.cu:188-211)."""
+    rng = np.random.default_rng(13)
+    src = cuda((rng.random((4000, 3), dtype=np.float32) - 0.5) * 0.5)
+    tgt = cuda((rng.random((2500, 3), dtype=np.float32) - 0.5) * 0.5)
+    co = T.gaussian_analytic_coeffs(0.1, 3, 32)
+    for A, n_in in [(T.GramMatrix(co, src, cutoff=4), 4000), (T.GramMatrix(co, src, tgt, cutoff=4), 4000)]:
+        x = cuda(make_values(rng, (n_in, 2), False))
+        before = _lib.launch_count()
+        y1 = A @ x
+        first = _lib.launch_count() - before
+        counts = []
+        for _ in range(3):
+            before = _lib.launch_count()
+            y = A @ x
+            counts.append(_lib.launch_count() - before)
+        assert max(counts) == min(counts) and first - counts[0] >= BINNING_LAUNCHES, (first, counts)
+        assert torch.equal(y, y1) or O.rel_l2(y.cpu().numpy(), y1.cpu().numpy()) < 1e-6
+        exact = T.ndft_fastsum(x, co, src, None if A.is_symmetric() else tgt)
+        assert O.rel_l2(y.cpu().numpy(), exact.cpu().numpy()) < 5e-4  # the NFFT's own error at m = 4
+        # the transposed matrix shares the binnings
+        before = _lib.launch_count()
+        A.T @ cuda(make_values(rng, (A.shape[1], 2), False))
+        assert _lib.launch_count() - before == counts[0]
+
+
+def test_batch_offsets_equal_batch_vector():
+    """`batch_ptr` (B + 1 offsets) instead of the per-point int64 vector: identical binning, identical result."""
+    rng = np.random.default_rng(14)
+    for d, N, m in [(3, 32, 4), (2, 32, 4), (1, 256, 8)]:
+        pos, batch = make_points(rng, d, 5, 700, ragged=True)
+        x = make_values(rng, (pos.shape[0], 2), False)
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(batch, minlength=5))]).astype(np.int64)
+        tp, tb, tx, tptr = cuda(pos), cuda(batch), cuda(x), cuda(ptr)
+        y1 = T.nfft_adjoint(tx, tp, tb, N, m)
+        y2 = T.nfft_adjoint(tx, tp, batch_ptr=tptr, N=N, m=m)
+        assert O.rel_l2(y2.cpu().numpy(), O.nfft_adjoint(x, pos, batch, N, m)) < TOL
+        assert O.rel_l2(y2.cpu().numpy(), y1.cpu().numpy()) < 2e-6
+        f2 = T.nfft_forward(y1, plan=T.NfftPlan(tp, batch_ptr=tptr), m=m, real_output=True)
+        assert O.rel_l2(f2.cpu().numpy(), O.nfft_forward(y1.cpu().numpy(), pos, batch, m, real_output=True)) < TOL
+
+
+def test_int64_index_variants_of_the_spectral_kernels():
+    """The spectral kernels switch to 64-bit index arithmetic when B*C*M^d >= 2^31 (e.g. N=512 in 3D with 8
+    grids); the variants are forced here on small transforms and must reproduce the oracle."""
+    rng = np.random.default_rng(15)
+    L = _lib.lib()
+    L.nfftb200_debug_force_int64(1)
+    try:
+        for d, N, m, C in [(1, 64, 4, 2), (2, 32, 4, 3), (3, 16, 3, 1)]:
+            pos, batch = make_points(rng, d, 2, 500)
+            for cplx in (False, True):
+                x = make_values(rng, (pos.shape[0], C), cplx)
+                for ro in (False, True):
+                    y = T.nfft_adjoint(cuda(x), cuda(pos), cuda(batch), N, m, real_output=ro)
+                    assert O.rel_l2(y.cpu().numpy(), O.nfft_adjoint(x, pos, batch, N, m, real_output=ro)) < TOL
+                    xh = make_values(rng, (2,) + (N,) * d + (C,), cplx)
+                    f = T.nfft_forward(cuda(xh), cuda(pos), cuda(batch), m, real_output=ro)
+                    assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(xh, pos, batch, m, real_output=ro)) < TOL
+                co = O.gaussian_interpolated_coeffs(0.15, d, N)
+                src = (pos * 0.5).astype(np.float32)
+                s_ = T.nfft_fastsum(cuda(x), cuda(co), cuda(src), batch=cuda(batch), cutoff=m)
+                assert O.rel_l2(s_.cpu().numpy(), O.nfft_fastsum(x, co, src, None, batch, batch, m=m)) < TOL
+    finally:
+        L.nfftb200_debug_force_int64(0)
+
+
+def test_fft_work_area_comes_from_the_callers_workspace():
+    """Two streams run the same cached cuFFT handle at once without sharing scratch, and the hidden
+    allocations of the handles stay small (the work areas live in the per-stream torch workspaces)."""
+    rng = np.random.default_rng(17)
+    d, N, m, B = 3, 64, 4, 2
+    pos, batch = make_points(rng, d, B, 20000)
+    x1, x2 = make_values(rng, (pos.shape[0], 1), False), make_values(rng, (pos.shape[0], 1), False)
+    tp, tb, t1, t2 = cuda(pos), cuda(batch), cuda(x1), cuda(x2)
+    T.nfft_adjoint(t1, tp, tb, N, m)  # make the handle
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            a = T.nfft_adjoint(t1, tp, tb, N, m, batch_size=B)
+        with torch.cuda.stream(s2):
+            b = T.nfft_adjoint(t2, tp, tb, N, m, batch_size=B)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    r1, r2 = O.nfft_adjoint(x1, pos, batch, N, m), O.nfft_adjoint(x2, pos, batch, N, m)
+    for a, b in outs:
+        assert O.rel_l2(a.cpu().numpy(), r1) < TOL and O.rel_l2(b.cpu().numpy(), r2) < TOL
+    assert _lib.lib().nfftb200_plan_cache_size() >= 1
 
 
 # ---------------------------------------------------------------------------------------------
@@ -429,9 +538,9 @@ def test_cuda_graph_capture_and_replay(d, N, m, B, n):
     tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
 
     def pair():
-        T.forget_sorted_points()
-        y = T.nfft_adjoint(tx, tp, tb, N, m, batch_size=B)  # batch_size: no batch[-1].item() sync
-        return y, T.nfft_forward(y, tp, tb, m, real_output=True, batch_size=B)
+        plan = T.NfftPlan(tp, tb, batch_size=B)  # batch_size: no batch[-1].item() sync; binned inside the capture
+        y = T.nfft_adjoint(tx, plan=plan, N=N, m=m)
+        return y, T.nfft_forward(y, plan=plan, m=m, real_output=True)
 
     graphed = T.GraphedTransforms(pair)  # warm-up on a side stream (plans, workspace), then the capture
     gy, gf = graphed.outputs
@@ -448,6 +557,11 @@ def test_cuda_graph_capture_and_replay(d, N, m, B, n):
     ref_y = O.nfft_adjoint(x2, pos2, batch, N, m)
     assert O.rel_l2(gy.cpu().numpy(), ref_y) < TOL
     assert O.rel_l2(gf.cpu().numpy(), O.nfft_forward(ref_y, pos2, batch, m, real_output=True)) < TOL
-    # eager calls after the replay see the changed tensors (their version moved): no stale sort
+    # eager calls after the replay bin the changed tensors themselves
     y3 = T.nfft_adjoint(tx, tp, tb, N, m)
     assert O.rel_l2(y3.cpu().numpy(), ref_y) < TOL
+    # while the graph lives the cuFFT handle cache is pinned; close() releases it
+    with pytest.warns(RuntimeWarning):
+        T.clear_caches()
+    graphed.close()
+    T.clear_caches()

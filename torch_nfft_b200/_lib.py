@@ -12,8 +12,8 @@ from ._build import LIB_PATH as _DEFAULT_LIB_PATH
 # development aid: NFFTB200_LIB selects an alternative build of the same library (A/B experiments)
 LIB_PATH = os.environ.get("NFFTB200_LIB", _DEFAULT_LIB_PATH)
 
-OP_ADJOINT, OP_FORWARD, OP_FASTSUM, OP_SPREAD, OP_GATHER, OP_SORT, OP_SPECTRAL = range(7)
-X_COMPLEX, Y_REAL, COEFFS_COMPLEX, SYMMETRIC, PRESORTED = 1, 2, 4, 8, 16
+OP_ADJOINT, OP_FORWARD, OP_FASTSUM, OP_SPREAD, OP_GATHER, OP_SORT, OP_SPECTRAL, OP_PLAN = range(8)
+X_COMPLEX, Y_REAL, COEFFS_COMPLEX, SYMMETRIC, PLANNED, BATCH_OFFSETS = 1, 2, 4, 8, 16, 32
 
 _lock = threading.Lock()
 _lib = None
@@ -25,6 +25,22 @@ _SIGNATURES = {
     "nfftb200_last_error": (ctypes.c_char_p, []),
     "nfftb200_launch_count": (_i64, []),
     "nfftb200_plan_cache_clear": (ctypes.c_int, []),
+    "nfftb200_plan_cache_pin": (ctypes.c_int, [_i32]),
+    "nfftb200_plan_cache_size": (ctypes.c_int, []),
+    "nfftb200_debug_force_int64": (None, [_i32]),
+    # (n, n_geom, d, N, m, B, C, flags)
+    "nfftb200_plan_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32]),
+    # (pos, batch, plan, plan_bytes, n, n_geom, d, N, m, B, C, flags, ws, ws_bytes, stream)
+    "nfftb200_plan_points": (_i32, [_vp, _vp, _vp, _sz, _i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
+    # (plan, n, n_geom, d, N, m, B, C, flags, flags_out_host, stream)
+    "nfftb200_plan_flags": (_i32, [_vp, _i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _vp]),
+    # (pos, x, batch, plan, plan_bytes, y, n, d, N, m, B, C, flags, ws, ws_bytes, stream)
+    "nfftb200_adjoint_planned": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
+    "nfftb200_forward_planned": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
+    # (src, tgt, x, coeffs, sb, tb, src_plan, src_plan_bytes, tgt_plan, tgt_plan_bytes, y, n_src, n_tgt, d, N, m, B, C,
+    #  flags, ws, ws_bytes, stream)
+    "nfftb200_fastsum_planned": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _i64, _i64, _i32, _i64, _i32,
+                                        _i64, _i64, _i32, _vp, _sz, _vp]),
     "nfftb200_profile_enable": (None, [_i32]),
     "nfftb200_profile_read": (_i32, [_vp, _vp]),
     "nfftb200_debug_geometry": (_i32, [_i32, _i64, _i32, _i64, _i64, _i32, _i64, _vp]),
@@ -35,10 +51,10 @@ _SIGNATURES = {
     # (src, tgt, x, coeffs, sb, tb, y, n_src, n_tgt, d, N, m, B, C, flags, ws, ws_bytes, stream)
     "nfftb200_fastsum": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32,
                                 _vp, _sz, _vp]),
-    # (pos, x, batch, grid, n, d, N, m, B, C, flags, ws, ws_bytes, stream)
-    "nfftb200_spread": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
-    # (pos, batch, grid, y, n, d, N, m, B, C, flags, ws, ws_bytes, stream)
-    "nfftb200_gather": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
+    # (pos, x, batch, plan, plan_bytes, grid, n, d, N, m, B, C, flags, ws, ws_bytes, stream)
+    "nfftb200_spread": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
+    # (pos, batch, plan, plan_bytes, grid, y, n, d, N, m, B, C, flags, ws, ws_bytes, stream)
+    "nfftb200_gather": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
     # (grid, y, d, N, m, B, C, flags, ws, ws_bytes, stream)
     "nfftb200_adjoint_finish": (_i32, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _sz, _vp]),
     # (xhat, grid, d, N, m, B, C, flags, ws, ws_bytes, stream)

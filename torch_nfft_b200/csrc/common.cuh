@@ -88,11 +88,12 @@ struct Geom {
 };
 
 struct SortPlan {
-    uint32_t* keys;         // [n]  tile key per point (input order)
+    uint32_t* keys;         // [n]  tile key per point (input order); sort scratch, null for a kept plan
     uint32_t* perm;         // [n]  stable permutation (sorted position -> input index)
     uint32_t* bin_start;    // [nbins+1]
     uint32_t* chunk_start;  // [nbins+1]; chunk_start[nbins] = number of work items
     uint4* items;           // [max_items] {bin, first point, one past last point, 0}; zero beyond the last item
+    uint32_t* flags;        // [kPlanFlagWords] flags[0] = points a window kernel found outside their tile (stale plan)
     long long nbins;
     long long max_items;
 };

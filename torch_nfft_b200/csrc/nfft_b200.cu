@@ -12,6 +12,7 @@
 #include "window_reg.cuh"
 #include "window_reg2d.cuh"
 #include "window1d.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <stdlib.h>
 
 #include <initializer_list>
@@ -36,11 +37,17 @@ static std::mutex g_prof_mutex;
 static std::vector<ProfSpan> g_prof_spans;
 static std::vector<cudaEvent_t> g_prof_pool;
 
+static const char* const kStageNames[] = {"nfftb200:sort",   "nfftb200:spread", "nfftb200:fft",      "nfftb200:unpack",
+                                          "nfftb200:pack",   "nfftb200:gather", "nfftb200:multiply", "nfftb200:memset"};
+
+// One pipeline stage: an NVTX range around its enqueue (visible to Nsight tools; a no-op without one attached)
+// and, while profiling is enabled, a pair of CUDA events on the caller's stream.
 struct ProfScope {
     ProfSpan span{};
     cudaStream_t st;
     bool on;
     ProfScope(int stage, cudaStream_t s) : st(s), on(g_prof_on) {
+        nvtxRangePushA(kStageNames[stage]);
         if (!on) return;
         std::lock_guard<std::mutex> lock(g_prof_mutex);
         for (cudaEvent_t* e : {&span.a, &span.b}) {
@@ -51,6 +58,7 @@ struct ProfScope {
         cudaEventRecord(span.a, st);
     }
     ~ProfScope() {
+        nvtxRangePop();
         if (!on) return;
         cudaEventRecord(span.b, st);
         std::lock_guard<std::mutex> lock(g_prof_mutex);
@@ -133,12 +141,34 @@ static void choose_strides(Geom& g) {
     g.sZ = it->second.second;
 }
 
+// SM count of the current device (148 on B200), cached per device; 148 without a usable device (host-only
+// size queries)
+static int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        (void)cudaGetLastError();
+        return 148;
+    }
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+        (void)cudaGetLastError();
+        return 148;
+    }
+    cached[dev].store(v, std::memory_order_relaxed);
+    return v;
+}
+
 static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, bool cplx, int64_t n_points) {
     if (d < 1 || d > 3) NF_FAIL(NFFTB200_ERR_INVALID, "dimension d=%d not in [1,3]", d);
     if (N < 2 || (N & 1)) NF_FAIL(NFFTB200_ERR_INVALID, "bandwidth N=%lld must be even and >= 2", (long long)N);
     if (m < 1 || m > kMaxCutoff) NF_FAIL(NFFTB200_ERR_INVALID, "cutoff m=%d not in [1,%d]", m, kMaxCutoff);
     if (B < 1 || C < 1) NF_FAIL(NFFTB200_ERR_INVALID, "batch size %lld / columns %lld must be >= 1", (long long)B, (long long)C);
     if (2 * N > (1 << 20)) NF_FAIL(NFFTB200_ERR_INVALID, "bandwidth N=%lld too large", (long long)N);
+    // the permutation, bin offsets and work items are 32-bit, launch grids are unsigned
+    if (n_points < 0 || n_points >= (1ll << 32) - 1)
+        NF_FAIL(NFFTB200_ERR_INVALID, "number of points %lld not in [0, 2^32 - 1)", (long long)n_points);
     g = Geom{};
     g.dim = d;
     g.N = (int)N;
@@ -206,16 +236,20 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     long long te = d == 1 ? g.P[0] : (d == 2 ? (long long)g.sY * g.P[1] : (long long)g.sZ * g.P[2]);
     g.tile_elems = (int)((te + 3) / 4 * 4);
 
-    long long pm = n_points / (148 * 8);
+    long long pm = n_points / (sm_count() * 8);
     g.pmax = (int)(pm < 256 ? 256 : (pm > 2048 ? 2048 : pm));
     if (g.use_reg == 1) g.pmax = kRegMaxPts;
     if (g.use_reg == 2) g.pmax = kReg2MaxPts;
     if (g.use_reg == 3) {
-        pm = n_points / (148 * 4);
+        pm = n_points / (sm_count() * 4);
         g.pmax = (int)(pm < 512 ? 512 : (pm > kW1MaxPts ? kW1MaxPts : pm));
     }
     int threads = (team + 31) / 32 * 32;
     g.spread_threads = threads < 64 ? 64 : threads;
+    // work items (one CTA each) and radix blocks must fit a launch grid
+    const long long nbins = (long long)g.B * g.tiles_per_batch;
+    if (n_points / g.pmax + (nbins < n_points ? nbins : n_points) + 1 >= (1ll << 31))
+        NF_FAIL(NFFTB200_ERR_INVALID, "too many work items for one launch");
     return NFFTB200_OK;
 }
 
@@ -260,12 +294,29 @@ static WindowKernel get_gather(int dim, int ncomp, int L) {
     return pick_gather<1, 0>(ncomp);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) and size, not per launch
+static std::mutex g_attr_mutex;
+static std::map<std::pair<int, const void*>, size_t> g_attr_smem;
+static int ensure_dynamic_smem(const void* kern, size_t smem) {
+    if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
+    int dev = 0;
+    NF_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    size_t& have = g_attr_smem[std::make_pair(dev, kern)];
+    if (smem > have) {
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    return NFFTB200_OK;
+}
+
 static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPlan& sp, cudaStream_t st) {
     a.perm = sp.perm;
     a.bin_start = sp.bin_start;
     a.chunk_start = sp.chunk_start;
     a.items = sp.items;
     a.nbins = sp.nbins;
+    a.flags = sp.flags;
     if (g.use_reg == 2) {
         // 2D: supercell 4 x 4 cells, up to 8 channels per pass (remaining channels in smaller passes)
         int ncomp = g.ncomp;
@@ -286,8 +337,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
             if (!kern) NF_FAIL(NFFTB200_ERR_INVALID, "no 2D register-stencil kernel for L=%d ncomp=%d", g.L, ncomp);
             const int nsc = ((g.T[0] + 3) / 4) * ((g.T[1] + 3) / 4);
             const size_t smem = reg2_smem_bytes(g, ncomp, spread, nsc, win_floats);
-            if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
-            NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
             NF_LAUNCH(kern, (unsigned)sp.max_items, kReg2Threads, smem, st, g, a);
         }
         return NFFTB200_OK;
@@ -309,8 +359,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
 #undef NF_W1_CASE
             if (!kern) NF_FAIL(NFFTB200_ERR_INVALID, "no 1D kernel for ncomp=%d", ncomp);
             const size_t smem = spread ? w1_spread_smem_bytes(g, ncomp) : w1_gather_smem_bytes(g, ncomp);
-            if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
-            NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
             NF_LAUNCH(kern, (unsigned)sp.max_items, spread ? kW1SpreadThreads : kW1Threads, smem, st, g, a);
         }
         return NFFTB200_OK;
@@ -336,8 +385,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         }
         const int nsc = ((g.T[0] + kRegSX - 1) / kRegSX) * ((g.T[1] + kRegSY - 1) / kRegSY) * ((g.T[2] + kRegSZ - 1) / kRegSZ);
         const size_t smem = reg_smem_bytes(g, nsc, win_floats);
-        if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
-        NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
         for (int k0 = 0; k0 < g.K; ++k0) {
             a.k0 = k0;
             NF_LAUNCH(kern, (unsigned)sp.max_items, kRegThreads, smem, st, g, a);
@@ -352,8 +400,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         a.k0 = k0;
         WindowKernel kern = spread ? get_spread(g.dim, ncomp, g.L) : get_gather(g.dim, ncomp, g.L);
         const size_t smem = spread ? spread_smem_bytes(g, ncomp) : gather_smem_bytes(g, ncomp);
-        if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
-        NF_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
         const unsigned grid = (unsigned)sp.max_items;
         const unsigned block = spread ? (unsigned)g.spread_threads : (unsigned)kGatherThreads;
         NF_LAUNCH(kern, grid, block, smem, st, g, a);
@@ -363,6 +410,13 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
 
 // ----------------------------------------------------------------------------------------
 // cuFFT plan cache (the reference creates and destroys a plan per call, core_cuda.cu:254-272)
+//
+// Plans are made with cufftSetAutoAllocation(0): their work area is NOT owned by cuFFT but handed in per
+// call from the caller's workspace (cufftSetWorkArea), so two streams (or an eager call next to a graph
+// replay) never share scratch, captured graphs only reference caller-owned memory plus the plan's own
+// twiddle tables, and the memory shows up in the caller's allocator.  The handle state (stream, work area)
+// is set and the transform enqueued under g_plan_mutex.  The cache is an LRU of kMaxPlans handles;
+// nfftb200_plan_cache_pin() forbids destroying handles while captured graphs may still use their tables.
 // ----------------------------------------------------------------------------------------
 struct PlanKey {
     int dev, dim, M, type;
@@ -371,21 +425,38 @@ struct PlanKey {
         return std::tie(dev, dim, M, type, batch) < std::tie(o.dev, o.dim, o.M, o.type, o.batch);
     }
 };
+struct PlanEntry {
+    cufftHandle handle;
+    size_t work;
+    unsigned long long tick;
+};
+constexpr size_t kMaxPlans = 24;
 static std::mutex g_plan_mutex;
-static std::map<PlanKey, cufftHandle> g_plans;
+static std::map<PlanKey, PlanEntry> g_plans;
+static unsigned long long g_plan_tick = 0;
+static int g_plan_pins = 0;
 
-static int get_plan(int dim, int M, long long batch, cufftType type, cufftHandle* out) {
+// caller holds g_plan_mutex
+static int get_plan_locked(int dim, int M, long long batch, cufftType type, PlanEntry** out) {
     int dev = 0;
     NF_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_plan_mutex);
     PlanKey key{dev, dim, M, (int)type, batch};
     auto it = g_plans.find(key);
     if (it != g_plans.end()) {
-        *out = it->second;
+        it->second.tick = ++g_plan_tick;
+        *out = &it->second;
         return NFFTB200_OK;
+    }
+    if (g_plans.size() >= kMaxPlans && g_plan_pins == 0) {  // evict the least recently used handle
+        auto lru = g_plans.begin();
+        for (auto jt = g_plans.begin(); jt != g_plans.end(); ++jt)
+            if (jt->second.tick < lru->second.tick) lru = jt;
+        cufftDestroy(lru->second.handle);
+        g_plans.erase(lru);
     }
     cufftHandle plan;
     NF_CUFFT(cufftCreate(&plan));
+    cufftResult r = cufftSetAutoAllocation(plan, 0);
     long long n[3] = {M, M, M};
     long long real_dist = 1, half_dist = 1;
     for (int a = 0; a < dim; ++a) real_dist *= M;
@@ -395,14 +466,64 @@ static int get_plan(int dim, int M, long long batch, cufftType type, cufftHandle
     if (type == CUFFT_R2C) odist = half_dist;
     if (type == CUFFT_C2R) idist = half_dist;
     size_t work = 0;
-    cufftResult r = cufftMakePlanMany64(plan, dim, n, nullptr, 1, idist, nullptr, 1, odist, type, batch, &work);
+    if (r == CUFFT_SUCCESS)
+        r = cufftMakePlanMany64(plan, dim, n, nullptr, 1, idist, nullptr, 1, odist, type, batch, &work);
     if (r != CUFFT_SUCCESS) {
         cufftDestroy(plan);
         NF_FAIL(NFFTB200_ERR_CUFFT, "cufftMakePlanMany64(dim=%d, M=%d, batch=%lld, type=%d) -> %d", dim, M, batch,
                 (int)type, (int)r);
     }
-    g_plans[key] = plan;
-    *out = plan;
+    PlanEntry e{plan, work, ++g_plan_tick};
+    *out = &g_plans.emplace(key, e).first->second;
+    return NFFTB200_OK;
+}
+
+// bytes of cuFFT work area the transforms of one op need (the maximum over the plans it runs); 0 when no
+// device is usable (host-only size queries): the op itself then fails with a clear message
+static size_t fft_work_bytes(const Geom& g, bool grid_cplx) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    size_t need = 0;
+    const long long batch = (long long)g.B * g.C;
+    PlanEntry* e = nullptr;
+    if (grid_cplx) {
+        if (get_plan_locked(g.dim, g.M, batch, CUFFT_C2C, &e) == NFFTB200_OK) need = e->work;
+    } else {
+        if (get_plan_locked(g.dim, g.M, batch, CUFFT_R2C, &e) == NFFTB200_OK) need = e->work;
+        if (get_plan_locked(g.dim, g.M, batch, CUFFT_C2R, &e) == NFFTB200_OK && e->work > need) need = e->work;
+    }
+    (void)cudaGetLastError();
+    if (e == nullptr) g_err[0] = 0;  // no usable device: not an error of a size query
+    return align_up(need);
+}
+
+struct FftWork {
+    void* ptr;
+    size_t bytes;
+};
+
+enum FftKind { FFT_R2C, FFT_C2R, FFT_C2C_INVERSE, FFT_C2C_FORWARD };
+
+// one transform of all B*C grids on the caller's stream with the caller's work area
+static int fft_exec(const Geom& g, FftKind kind, void* in, void* out, const FftWork& work, cudaStream_t st) {
+    const cufftType type = kind == FFT_R2C ? CUFFT_R2C : (kind == FFT_C2R ? CUFFT_C2R : CUFFT_C2C);
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    PlanEntry* e = nullptr;
+    NF_TRY(get_plan_locked(g.dim, g.M, (long long)g.B * g.C, type, &e));
+    if (e->work > work.bytes)
+        NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small for the cuFFT work area: %zu < %zu", work.bytes, e->work);
+    NF_CUFFT(cufftSetStream(e->handle, st));
+    if (e->work > 0) NF_CUFFT(cufftSetWorkArea(e->handle, work.ptr));
+    ProfScope ps(ST_FFT, st);
+    switch (kind) {
+        case FFT_R2C: NF_CUFFT(cufftExecR2C(e->handle, (cufftReal*)in, (cufftComplex*)out)); break;
+        case FFT_C2R: NF_CUFFT(cufftExecC2R(e->handle, (cufftComplex*)in, (cufftReal*)out)); break;
+        case FFT_C2C_INVERSE:  // sign +, core_cuda.cu:267
+            NF_CUFFT(cufftExecC2C(e->handle, (cufftComplex*)in, (cufftComplex*)out, CUFFT_INVERSE));
+            break;
+        default:               // sign -, core_cuda.cu:445
+            NF_CUFFT(cufftExecC2C(e->handle, (cufftComplex*)in, (cufftComplex*)out, CUFFT_FORWARD));
+            break;
+    }
     return NFFTB200_OK;
 }
 
@@ -426,20 +547,12 @@ static unsigned blocks_for(long long total, int threads = 256) { return (unsigne
 // ----------------------------------------------------------------------------------------
 // stage implementations
 // ----------------------------------------------------------------------------------------
-static int do_spread(const Geom& g, const float* pos, const float* x, const int64_t* batch, float* grid, long long n,
-                     char* sort_ws, SortPlan* sp_out, cudaStream_t st, bool presorted = false) {
+static int do_spread(const Geom& g, const float* pos, const float* x, float* grid, long long n, const SortPlan& sp,
+                     cudaStream_t st) {
     {
         ProfScope ps(ST_MEMSET, st);
         NF_CUDA(cudaMemsetAsync(grid, 0, (size_t)g.B * g.C * g.Md * (g.cplx ? 8 : 4), st));
     }
-    SortPlan sp{};
-    if (presorted) {
-        sort_plan_pointers(n, g, sort_ws, &sp);
-    } else {
-        ProfScope ps(ST_SORT, st);
-        NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
-    }
-    if (sp_out) *sp_out = sp;
     if (n == 0) return NFFTB200_OK;
     WindowArgs a{};
     a.pos = pos;
@@ -449,24 +562,21 @@ static int do_spread(const Geom& g, const float* pos, const float* x, const int6
     return launch_window(true, g, a, sp, st);
 }
 
-static int do_gather(const Geom& g, const float* pos, const int64_t* batch, const float* grid, float* y, long long n,
-                     char* sort_ws, const SortPlan* presorted, cudaStream_t st, bool presorted_ws = false) {
+static int do_gather(const Geom& g, const float* pos, const float* grid, float* y, long long n, const SortPlan& sp,
+                     cudaStream_t st) {
     if (n == 0) return NFFTB200_OK;
-    SortPlan sp{};
-    if (presorted) {
-        sp = *presorted;
-    } else if (presorted_ws) {
-        sort_plan_pointers(n, g, sort_ws, &sp);
-    } else {
-        ProfScope ps(ST_SORT, st);
-        NF_TRY(sort_points(pos, batch, n, g, sort_ws, &sp, st));
-    }
     WindowArgs a{};
     a.pos = pos;
     a.yout = y;
     a.grid = const_cast<float*>(grid);
     ProfScope ps(ST_GATHER, st);
     return launch_window(false, g, a, sp, st);
+}
+
+static int do_sort(const Geom& g, const float* pos, const int64_t* batch, bool offsets, long long n, char* scratch,
+                   char* plan_mem, SortPlan* sp, cudaStream_t st) {
+    ProfScope ps(ST_SORT, st);
+    return sort_points(pos, batch, offsets, n, g, scratch, plan_mem, sp, st);
 }
 
 // spectral kernels use 32-bit index arithmetic whenever every element index fits 31 bits
@@ -517,8 +627,12 @@ static int launch_multiply_t(const Geom& g, bool half, bool creal, float2* spec,
     return NFFTB200_OK;
 }
 
+// tests: force the 64-bit index variants of the spectral kernels (nfftb200_debug_force_int64)
+static std::atomic<int> g_force_int64{0};
+
 static bool fits_int32(const Geom& g) {
     // largest index any spectral kernel forms: complex grid elements plus one block of slack
+    if (g_force_int64.load(std::memory_order_relaxed)) return false;
     return (long long)g.B * g.C * g.Md < (1ll << 31) - 1024;
 }
 template <int DIM>
@@ -541,112 +655,80 @@ static int launch_multiply(const Geom& g, bool half, bool creal, float2* spec, c
     (g.dim == 1 ? fn<1>(__VA_ARGS__) : (g.dim == 2 ? fn<2>(__VA_ARGS__) : fn<3>(__VA_ARGS__)))
 
 // grid (real: [BC][M^d] float, complex: [BC][M^d] float2) -> y.  spec: scratch for the half spectrum.
-static int do_adjoint_finish(const Geom& g, float* grid, float* y, bool real_out, float2* spec, cudaStream_t st) {
-    cufftHandle plan;
+static int do_adjoint_finish(const Geom& g, float* grid, float* y, bool real_out, float2* spec, const FftWork& fw,
+                             cudaStream_t st) {
     if (!g.cplx) {
-        NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_R2C, &plan));
-        NF_CUFFT(cufftSetStream(plan, st));
-        {
-            ProfScope ps(ST_FFT, st);
-            NF_CUFFT(cufftExecR2C(plan, grid, reinterpret_cast<cufftComplex*>(spec)));
-        }
+        NF_TRY(fft_exec(g, FFT_R2C, grid, spec, fw, st));
         ProfScope ps(ST_UNPACK, st);
         return NF_DIM_DISPATCH(launch_unpack, g, true, real_out, spec, y, st);
     }
-    NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2C, &plan));
-    NF_CUFFT(cufftSetStream(plan, st));
-    {
-        ProfScope ps(ST_FFT, st);
-        NF_CUFFT(cufftExecC2C(plan, reinterpret_cast<cufftComplex*>(grid), reinterpret_cast<cufftComplex*>(grid),
-                              CUFFT_INVERSE));  // sign +, core_cuda.cu:267
-    }
+    NF_TRY(fft_exec(g, FFT_C2C_INVERSE, grid, grid, fw, st));
     ProfScope ps(ST_UNPACK, st);
     return NF_DIM_DISPATCH(launch_unpack, g, false, real_out, reinterpret_cast<const float2*>(grid), y, st);
 }
 
 // xhat -> grid.  real_out: grid is float (C2R), else float2 (C2C sign -).
 static int do_forward_begin(const Geom& g, const float* xhat, bool xreal, bool real_out, float* grid, float2* spec,
-                            cudaStream_t st) {
-    cufftHandle plan;
+                            const FftWork& fw, cudaStream_t st) {
     if (real_out) {
         {
             ProfScope ps(ST_PACK, st);
             NF_TRY(NF_DIM_DISPATCH(launch_pack, g, true, xreal, xhat, spec, st));
         }
-        NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2R, &plan));
-        NF_CUFFT(cufftSetStream(plan, st));
-        ProfScope ps(ST_FFT, st);
-        NF_CUFFT(cufftExecC2R(plan, reinterpret_cast<cufftComplex*>(spec), grid));
-        return NFFTB200_OK;
+        return fft_exec(g, FFT_C2R, spec, grid, fw, st);
     }
     {
         ProfScope ps(ST_PACK, st);
         NF_TRY(NF_DIM_DISPATCH(launch_pack, g, false, xreal, xhat, reinterpret_cast<float2*>(grid), st));
     }
-    NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2C, &plan));
-    NF_CUFFT(cufftSetStream(plan, st));
-    ProfScope ps(ST_FFT, st);
-    NF_CUFFT(cufftExecC2C(plan, reinterpret_cast<cufftComplex*>(grid), reinterpret_cast<cufftComplex*>(grid),
-                          CUFFT_FORWARD));  // sign -, core_cuda.cu:445
-    return NFFTB200_OK;
+    return fft_exec(g, FFT_C2C_FORWARD, grid, grid, fw, st);
 }
 
 static int do_fastsum_middle(const Geom& g, float* grid, const float* coeffs, bool creal, float2* spec,
-                             cudaStream_t st) {
-    cufftHandle plan;
+                             const FftWork& fw, cudaStream_t st) {
     if (!g.cplx) {
-        NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_R2C, &plan));
-        NF_CUFFT(cufftSetStream(plan, st));
-        {
-            ProfScope ps(ST_FFT, st);
-            NF_CUFFT(cufftExecR2C(plan, grid, reinterpret_cast<cufftComplex*>(spec)));
-        }
+        NF_TRY(fft_exec(g, FFT_R2C, grid, spec, fw, st));
         {
             ProfScope ps(ST_MULTIPLY, st);
             NF_TRY(NF_DIM_DISPATCH(launch_multiply, g, true, creal, spec, coeffs, st));
         }
-        NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2R, &plan));
-        NF_CUFFT(cufftSetStream(plan, st));
-        ProfScope ps(ST_FFT, st);
-        NF_CUFFT(cufftExecC2R(plan, reinterpret_cast<cufftComplex*>(spec), grid));
-        return NFFTB200_OK;
+        return fft_exec(g, FFT_C2R, spec, grid, fw, st);
     }
-    NF_TRY(get_plan(g.dim, g.M, (long long)g.B * g.C, CUFFT_C2C, &plan));
-    NF_CUFFT(cufftSetStream(plan, st));
-    cufftComplex* gc = reinterpret_cast<cufftComplex*>(grid);
-    {
-        ProfScope ps(ST_FFT, st);
-        NF_CUFFT(cufftExecC2C(plan, gc, gc, CUFFT_INVERSE));
-    }
+    NF_TRY(fft_exec(g, FFT_C2C_INVERSE, grid, grid, fw, st));
     {
         ProfScope ps(ST_MULTIPLY, st);
         NF_TRY(NF_DIM_DISPATCH(launch_multiply, g, false, creal, reinterpret_cast<float2*>(grid), coeffs, st));
     }
-    ProfScope ps(ST_FFT, st);
-    NF_CUFFT(cufftExecC2C(plan, gc, gc, CUFFT_FORWARD));
-    return NFFTB200_OK;
+    return fft_exec(g, FFT_C2C_FORWARD, grid, grid, fw, st);
 }
 
 // workspace carving ------------------------------------------------------------------------
+// [sort scratch | point plan(s) | grid | half spectrum | cuFFT work area]; pieces an op does not need are empty
 struct Workspace {
-    size_t sort, grid, spec, total;
+    size_t scratch, plan_a, plan_b, grid, spec, fft, fft_bytes, total;
 };
 
-// which pieces an op needs: sort scratch for max(n_src, n_tgt) points, a grid, a half spectrum
-static Workspace ws_layout(int op, const Geom& g, long long n_src, long long n_tgt, bool grid_cplx, bool need_spec) {
+static Workspace ws_layout(const Geom& g, long long n_sort_a, long long n_sort_b, bool need_grid, bool grid_cplx,
+                           bool need_spec, bool need_fft) {
     Workspace w{};
     size_t off = 0;
-    w.sort = off;
-    const bool need_sort = op != -1;
-    if (need_sort) {
-        Geom gs = g;
-        size_t a = sort_layout(n_src, gs).total, b = sort_layout(n_tgt, gs).total;
+    w.scratch = off;
+    if (n_sort_a >= 0 || n_sort_b >= 0) {
+        const size_t a = n_sort_a >= 0 ? sort_layout(n_sort_a, g).total : 0;
+        const size_t b = n_sort_b >= 0 ? sort_layout(n_sort_b, g).total : 0;
         off += align_up(a > b ? a : b);
     }
+    w.plan_a = off;
+    if (n_sort_a >= 0) off += align_up(plan_layout(n_sort_a, g).total);
+    w.plan_b = off;
+    if (n_sort_b >= 0) off += align_up(plan_layout(n_sort_b, g).total);
     w.grid = off;
-    if (op == NFFTB200_OP_ADJOINT || op == NFFTB200_OP_FORWARD || op == NFFTB200_OP_FASTSUM) off += grid_bytes(g, grid_cplx);
+    if (need_grid) off += grid_bytes(g, grid_cplx);
     w.spec = off;
     if (need_spec) off += half_bytes(g);
+    w.fft = off;
+    w.fft_bytes = need_fft ? fft_work_bytes(g, grid_cplx) : 0;
+    off += w.fft_bytes;
     w.total = off;
     return w;
 }
@@ -660,7 +742,7 @@ using namespace nfftb200;
 
 extern "C" {
 
-int nfftb200_version(void) { return 100; }
+int nfftb200_version(void) { return 200; }
 const char* nfftb200_last_error(void) { return g_err; }
 int64_t nfftb200_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -673,6 +755,8 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
     for (int i = 0; i < 21; ++i) out[i] = v[i];
     return NFFTB200_OK;
 }
+
+void nfftb200_debug_force_int64(int on) { g_force_int64.store(on ? 1 : 0); }
 
 #ifdef NFFT_PHASE_TIMING
 // debug build only: out[2][24] = accumulated clock64() phase lengths of the register-stencil kernels
@@ -715,9 +799,23 @@ int nfftb200_profile_read(double* ms_out, int64_t* count_out) {
 
 int nfftb200_plan_cache_clear(void) {
     std::lock_guard<std::mutex> lock(g_plan_mutex);
-    for (auto& kv : g_plans) cufftDestroy(kv.second);
+    if (g_plan_pins > 0)
+        NF_FAIL(NFFTB200_ERR_INVALID, "cuFFT plan cache is pinned by %d live CUDA graph(s): not cleared", g_plan_pins);
+    for (auto& kv : g_plans) cufftDestroy(kv.second.handle);
     g_plans.clear();
     return NFFTB200_OK;
+}
+
+int nfftb200_plan_cache_pin(int delta) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    g_plan_pins += delta;
+    if (g_plan_pins < 0) g_plan_pins = 0;
+    return g_plan_pins;
+}
+
+int nfftb200_plan_cache_size(void) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    return (int)g_plans.size();
 }
 
 // how each public op uses the grid: (grid is complex?, needs half-spectrum scratch?)
@@ -731,19 +829,59 @@ static void op_modes(int op, int flags, bool* grid_cplx, bool* need_spec) {
     }
 }
 
-size_t nfftb200_workspace_bytes(int op, int64_t n_src, int64_t n_tgt, int d, int64_t N, int m, int64_t B, int64_t C,
-                                int flags) {
+// the layout of a public op (shared by nfftb200_workspace_bytes and the op itself)
+static int op_layout(int op, long long n_src, long long n_tgt, int d, int64_t N, int m, int64_t B, int64_t C, int flags,
+                     Geom* g, Workspace* w) {
     bool gc, ns;
     op_modes(op, flags, &gc, &ns);
-    Geom g;
     const long long np = n_src > n_tgt ? n_src : n_tgt;
-    if (make_geom(g, d, N, m, B, C, gc, np) != NFFTB200_OK) return 0;
-    if (op == NFFTB200_OP_SPREAD || op == NFFTB200_OP_GATHER || op == NFFTB200_OP_SORT) {
-        return align_up(sort_layout(np, g).total) + 256;
+    NF_TRY(make_geom(*g, d, N, m, B, C, gc, np));
+    const bool planned = flags & NFFTB200_PLANNED;  // the caller brings the point plan(s): no sort regions
+    const bool sym = (flags & NFFTB200_SYMMETRIC) && n_src == n_tgt;
+    switch (op) {
+        case NFFTB200_OP_ADJOINT: *w = ws_layout(*g, planned ? -1 : n_src, -1, true, gc, ns, true); break;
+        case NFFTB200_OP_FORWARD: *w = ws_layout(*g, planned ? -1 : n_tgt, -1, true, gc, ns, true); break;
+        case NFFTB200_OP_FASTSUM:
+            *w = ws_layout(*g, planned ? -1 : n_src, planned || sym ? -1 : n_tgt, true, gc, ns, true);
+            break;
+        case NFFTB200_OP_SPREAD:
+        case NFFTB200_OP_GATHER: *w = ws_layout(*g, planned ? -1 : np, -1, false, gc, false, false); break;
+        case NFFTB200_OP_SORT: *w = ws_layout(*g, np, -1, false, gc, false, false); break;
+        case NFFTB200_OP_PLAN: {  // nfftb200_plan_points: scratch only, the plan lives in the caller's plan buffer
+            *w = Workspace{};
+            w->total = align_up(sort_layout(np, *g).total);
+            break;
+        }
+        case NFFTB200_OP_SPECTRAL: {  // adjoint_finish / forward_begin / fastsum_middle: spectrum + FFT work area
+            Geom gr = *g;
+            *w = ws_layout(gr, -1, -1, false, flags & NFFTB200_X_COMPLEX, true, false);
+            // the three stage helpers run R2C / C2R / C2C depending on their own flags: provide for all of them
+            size_t f = fft_work_bytes(*g, false);
+            Geom gcx = *g;
+            gcx.cplx = 1;
+            const size_t f2 = fft_work_bytes(gcx, true);
+            w->fft = w->total;
+            w->fft_bytes = f > f2 ? f : f2;
+            w->total += w->fft_bytes;
+            break;
+        }
+        default: NF_FAIL(NFFTB200_ERR_INVALID, "unknown op %d", op);
     }
-    if (op == NFFTB200_OP_SPECTRAL) return half_bytes(g) + 256;
-    // stage-only helpers: adjoint_finish / forward_begin / fastsum_middle need only the spectrum
-    return ws_layout(op, g, n_src, n_tgt, gc, true).total + 256;
+    return NFFTB200_OK;
+}
+
+size_t nfftb200_workspace_bytes(int op, int64_t n_src, int64_t n_tgt, int d, int64_t N, int m, int64_t B, int64_t C,
+                                int flags) {
+    Geom g;
+    Workspace w;
+    if (op_layout(op, n_src, n_tgt, d, N, m, B, C, flags, &g, &w) != NFFTB200_OK) return 0;
+    return w.total + 256;
+}
+
+size_t nfftb200_plan_bytes(int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B, int64_t C, int flags) {
+    Geom g;
+    if (make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n_geom > n ? n_geom : n) != NFFTB200_OK) return 0;
+    return align_up(plan_layout(n, g).total) + 256;
 }
 
 #define NF_REQUIRE(cond, msg)                                  \
@@ -751,79 +889,187 @@ size_t nfftb200_workspace_bytes(int op, int64_t n_src, int64_t n_tgt, int d, int
         if (!(cond)) NF_FAIL(NFFTB200_ERR_INVALID, "%s", msg); \
     } while (0)
 
-static char* align_ptr(void* p) { return (char*)(((uintptr_t)p + 255) / 256 * 256); }
+static char* align_ptr(const void* p) { return (char*)(((uintptr_t)p + 255) / 256 * 256); }
+
+#define NF_CHECK_WS(w, bytes)                                                                                     \
+    do {                                                                                                          \
+        if ((bytes) < (w).total + 256)                                                                            \
+            NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small: %zu < %zu", (size_t)(bytes), (w).total + 256);  \
+    } while (0)
+
+// resolves the point plan of an op: the caller's kept plan (NFFTB200_PLANNED) or a fresh sort into the workspace
+static int resolve_plan(const Geom& g, int flags, const float* pos, const int64_t* batch, long long n, const void* plan,
+                        size_t plan_bytes, char* ws, size_t scratch_off, size_t plan_off, SortPlan* sp, cudaStream_t st) {
+    if (flags & NFFTB200_PLANNED) {
+        NF_REQUIRE(plan != nullptr, "NFFTB200_PLANNED without a plan buffer");
+        if (plan_bytes < plan_layout(n, g).total)
+            NF_FAIL(NFFTB200_ERR_WORKSPACE, "plan buffer too small: %zu < %zu", plan_bytes, plan_layout(n, g).total);
+        sort_plan_pointers(n, g, align_ptr(plan), sp);
+        return NFFTB200_OK;
+    }
+    return do_sort(g, pos, batch, flags & NFFTB200_BATCH_OFFSETS, n, ws + scratch_off, ws + plan_off, sp, st);
+}
+
+int nfftb200_plan_points(const float* pos, const int64_t* batch, void* plan, size_t plan_bytes, int64_t n, int64_t n_geom,
+                         int d, int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    NF_REQUIRE(n >= 0 && plan && workspace && (n == 0 || pos), "nfftb200_plan_points: null pointer");
+    Geom g;
+    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n_geom > n ? n_geom : n));
+    if (plan_bytes < align_up(plan_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "plan buffer too small");
+    if (workspace_bytes < align_up(sort_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
+    SortPlan sp{};
+    return do_sort(g, pos, batch, flags & NFFTB200_BATCH_OFFSETS, n, align_ptr(workspace), align_ptr(plan), &sp,
+                   (cudaStream_t)stream);
+}
+
+// flags_out[8] (host): flags_out[0] = points the window kernels found outside their tile since the plan was made
+// (non-zero: the positions changed after nfftb200_plan_points).  Synchronises the stream.
+int nfftb200_plan_flags(const void* plan, int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B, int64_t C,
+                        int flags, uint32_t* flags_out, void* stream) {
+    NF_REQUIRE(plan && flags_out, "nfftb200_plan_flags: null pointer");
+    Geom g;
+    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n_geom > n ? n_geom : n));
+    SortPlan sp{};
+    sort_plan_pointers(n, g, align_ptr(plan), &sp);
+    cudaStream_t st = (cudaStream_t)stream;
+    NF_CUDA(cudaMemcpyAsync(flags_out, sp.flags, kPlanFlagWords * 4, cudaMemcpyDeviceToHost, st));
+    NF_CUDA(cudaStreamSynchronize(st));
+    return NFFTB200_OK;
+}
 
 int nfftb200_adjoint(const float* pos, const void* x, const int64_t* batch, void* y, int64_t n, int d, int64_t N, int m,
                      int64_t B, int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+    return nfftb200_adjoint_planned(pos, x, batch, nullptr, 0, y, n, d, N, m, B, C, flags & ~NFFTB200_PLANNED, workspace,
+                                    workspace_bytes, stream);
+}
+
+int nfftb200_adjoint_planned(const float* pos, const void* x, const int64_t* batch, const void* plan, size_t plan_bytes,
+                             void* y, int64_t n, int d, int64_t N, int m, int64_t B, int64_t C, int flags,
+                             void* workspace, size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n >= 0 && y && workspace && (n == 0 || (pos && x)), "nfftb200_adjoint: null pointer");
-    const bool xc = flags & NFFTB200_X_COMPLEX, yr = flags & NFFTB200_Y_REAL;
+    const bool yr = flags & NFFTB200_Y_REAL;
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, xc, n));
-    const Workspace w = ws_layout(NFFTB200_OP_ADJOINT, g, n, 0, xc, true);
-    if (workspace_bytes < w.total + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total + 256);
+    Workspace w;
+    NF_TRY(op_layout(NFFTB200_OP_ADJOINT, n, 0, d, N, m, B, C, flags, &g, &w));
+    NF_CHECK_WS(w, workspace_bytes);
     char* ws = align_ptr(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     float* grid = (float*)(ws + w.grid);
-    NF_TRY(do_spread(g, pos, (const float*)x, batch, grid, n, ws + w.sort, nullptr, st, flags & NFFTB200_PRESORTED));
-    return do_adjoint_finish(g, grid, (float*)y, yr, (float2*)(ws + w.spec), st);
+    SortPlan sp{};
+    NF_TRY(resolve_plan(g, flags, pos, batch, n, plan, plan_bytes, ws, w.scratch, w.plan_a, &sp, st));
+    NF_TRY(do_spread(g, pos, (const float*)x, grid, n, sp, st));
+    return do_adjoint_finish(g, grid, (float*)y, yr, (float2*)(ws + w.spec), FftWork{ws + w.fft, w.fft_bytes}, st);
 }
 
 int nfftb200_forward(const float* pos, const void* xhat, const int64_t* batch, void* y, int64_t n, int d, int64_t N,
                      int m, int64_t B, int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+    return nfftb200_forward_planned(pos, xhat, batch, nullptr, 0, y, n, d, N, m, B, C, flags & ~NFFTB200_PLANNED,
+                                    workspace, workspace_bytes, stream);
+}
+
+int nfftb200_forward_planned(const float* pos, const void* xhat, const int64_t* batch, const void* plan,
+                             size_t plan_bytes, void* y, int64_t n, int d, int64_t N, int m, int64_t B, int64_t C,
+                             int flags, void* workspace, size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n >= 0 && xhat && workspace && (n == 0 || (pos && y)), "nfftb200_forward: null pointer");
     const bool xc = flags & NFFTB200_X_COMPLEX, yr = flags & NFFTB200_Y_REAL;
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, !yr, n));
-    const Workspace w = ws_layout(NFFTB200_OP_FORWARD, g, 0, n, !yr, true);
-    if (workspace_bytes < w.total + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total + 256);
+    Workspace w;
+    NF_TRY(op_layout(NFFTB200_OP_FORWARD, 0, n, d, N, m, B, C, flags, &g, &w));
+    NF_CHECK_WS(w, workspace_bytes);
     if (n == 0) return NFFTB200_OK;
     char* ws = align_ptr(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     float* grid = (float*)(ws + w.grid);
-    NF_TRY(do_forward_begin(g, (const float*)xhat, !xc, yr, grid, (float2*)(ws + w.spec), st));
-    return do_gather(g, pos, batch, grid, (float*)y, n, ws + w.sort, nullptr, st, flags & NFFTB200_PRESORTED);
+    NF_TRY(do_forward_begin(g, (const float*)xhat, !xc, yr, grid, (float2*)(ws + w.spec),
+                            FftWork{ws + w.fft, w.fft_bytes}, st));
+    SortPlan sp{};
+    NF_TRY(resolve_plan(g, flags, pos, batch, n, plan, plan_bytes, ws, w.scratch, w.plan_a, &sp, st));
+    return do_gather(g, pos, grid, (float*)y, n, sp, st);
 }
 
 int nfftb200_fastsum(const float* sources, const float* targets, const void* x, const void* coeffs,
                      const int64_t* source_batch, const int64_t* target_batch, void* y, int64_t n_src, int64_t n_tgt,
                      int d, int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace, size_t workspace_bytes,
                      void* stream) {
+    return nfftb200_fastsum_planned(sources, targets, x, coeffs, source_batch, target_batch, nullptr, 0, nullptr, 0, y,
+                                    n_src, n_tgt, d, N, m, B, C, flags & ~NFFTB200_PLANNED, workspace, workspace_bytes,
+                                    stream);
+}
+
+int nfftb200_fastsum_planned(const float* sources, const float* targets, const void* x, const void* coeffs,
+                             const int64_t* source_batch, const int64_t* target_batch, const void* source_plan,
+                             size_t source_plan_bytes, const void* target_plan, size_t target_plan_bytes, void* y,
+                             int64_t n_src, int64_t n_tgt, int d, int64_t N, int m, int64_t B, int64_t C, int flags,
+                             void* workspace, size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n_src >= 0 && n_tgt >= 0 && coeffs && workspace, "nfftb200_fastsum: null pointer");
     NF_REQUIRE(n_src == 0 || (sources && x), "nfftb200_fastsum: null sources/x");
     NF_REQUIRE(n_tgt == 0 || (targets && y), "nfftb200_fastsum: null targets/y");
-    const bool xc = flags & NFFTB200_X_COMPLEX;
     const bool creal = !(flags & NFFTB200_COEFFS_COMPLEX);
     const bool sym = (flags & NFFTB200_SYMMETRIC) && n_src == n_tgt;
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, xc, n_src > n_tgt ? n_src : n_tgt));
-    const Workspace w = ws_layout(NFFTB200_OP_FASTSUM, g, n_src, n_tgt, xc, true);
-    if (workspace_bytes < w.total + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total + 256);
+    Workspace w;
+    NF_TRY(op_layout(NFFTB200_OP_FASTSUM, n_src, n_tgt, d, N, m, B, C, flags, &g, &w));
+    NF_CHECK_WS(w, workspace_bytes);
     if (n_tgt == 0) return NFFTB200_OK;
     char* ws = align_ptr(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     float* grid = (float*)(ws + w.grid);
-    SortPlan sp{};
-    NF_TRY(do_spread(g, sources, (const float*)x, source_batch, grid, n_src, ws + w.sort, &sp, st));
-    NF_TRY(do_fastsum_middle(g, grid, (const float*)coeffs, creal, (float2*)(ws + w.spec), st));
-    return do_gather(g, targets, target_batch, grid, (float*)y, n_tgt, ws + w.sort, sym ? &sp : nullptr, st);
+    SortPlan sp_src{}, sp_tgt{};
+    NF_TRY(resolve_plan(g, flags, sources, source_batch, n_src, source_plan, source_plan_bytes, ws, w.scratch, w.plan_a,
+                        &sp_src, st));
+    NF_TRY(do_spread(g, sources, (const float*)x, grid, n_src, sp_src, st));
+    NF_TRY(do_fastsum_middle(g, grid, (const float*)coeffs, creal, (float2*)(ws + w.spec),
+                             FftWork{ws + w.fft, w.fft_bytes}, st));
+    if (sym) {
+        sp_tgt = sp_src;
+    } else {
+        NF_TRY(resolve_plan(g, flags, targets, target_batch, n_tgt, target_plan, target_plan_bytes, ws, w.scratch,
+                            w.plan_b, &sp_tgt, st));
+    }
+    return do_gather(g, targets, grid, (float*)y, n_tgt, sp_tgt, st);
 }
 
-int nfftb200_spread(const float* pos, const void* x, const int64_t* batch, void* grid, int64_t n, int d, int64_t N,
-                    int m, int64_t B, int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+int nfftb200_spread(const float* pos, const void* x, const int64_t* batch, const void* plan, size_t plan_bytes,
+                    void* grid, int64_t n, int d, int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace,
+                    size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n >= 0 && grid && workspace && (n == 0 || (pos && x)), "nfftb200_spread: null pointer");
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    if (workspace_bytes < align_up(sort_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
-    return do_spread(g, pos, (const float*)x, batch, (float*)grid, n, align_ptr(workspace), nullptr, (cudaStream_t)stream);
+    Workspace w;
+    NF_TRY(op_layout(NFFTB200_OP_SPREAD, n, 0, d, N, m, B, C, flags, &g, &w));
+    NF_CHECK_WS(w, workspace_bytes);
+    char* ws = align_ptr(workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    SortPlan sp{};
+    NF_TRY(resolve_plan(g, flags, pos, batch, n, plan, plan_bytes, ws, w.scratch, w.plan_a, &sp, st));
+    return do_spread(g, pos, (const float*)x, (float*)grid, n, sp, st);
 }
 
-int nfftb200_gather(const float* pos, const int64_t* batch, const void* grid, void* y, int64_t n, int d, int64_t N,
-                    int m, int64_t B, int64_t C, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+int nfftb200_gather(const float* pos, const int64_t* batch, const void* plan, size_t plan_bytes, const void* grid,
+                    void* y, int64_t n, int d, int64_t N, int m, int64_t B, int64_t C, int flags, void* workspace,
+                    size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n >= 0 && grid && workspace && (n == 0 || (pos && y)), "nfftb200_gather: null pointer");
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    if (workspace_bytes < align_up(sort_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
-    return do_gather(g, pos, batch, (const float*)grid, (float*)y, n, align_ptr(workspace), nullptr, (cudaStream_t)stream);
+    Workspace w;
+    NF_TRY(op_layout(NFFTB200_OP_GATHER, 0, n, d, N, m, B, C, flags, &g, &w));
+    NF_CHECK_WS(w, workspace_bytes);
+    char* ws = align_ptr(workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    SortPlan sp{};
+    NF_TRY(resolve_plan(g, flags, pos, batch, n, plan, plan_bytes, ws, w.scratch, w.plan_a, &sp, st));
+    return do_gather(g, pos, (const float*)grid, (float*)y, n, sp, st);
+}
+
+// the three spectral stage helpers share one layout: [half spectrum | cuFFT work area]
+static int spectral_layout(const Geom& g, void* workspace, size_t workspace_bytes, float2** spec, FftWork* fw) {
+    const size_t hb = half_bytes(g);
+    if (workspace_bytes < hb + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
+    char* ws = align_ptr(workspace);
+    *spec = (float2*)ws;
+    fw->ptr = ws + hb;
+    const size_t used = (size_t)(ws - (char*)workspace) + hb;
+    fw->bytes = workspace_bytes > used ? workspace_bytes - used : 0;
+    return NFFTB200_OK;
 }
 
 int nfftb200_adjoint_finish(void* grid, void* y, int d, int64_t N, int m, int64_t B, int64_t C, int flags,
@@ -832,9 +1078,10 @@ int nfftb200_adjoint_finish(void* grid, void* y, int d, int64_t N, int m, int64_
     const bool xc = flags & NFFTB200_X_COMPLEX;
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, xc, 0));
-    if (workspace_bytes < half_bytes(g) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
-    return do_adjoint_finish(g, (float*)grid, (float*)y, flags & NFFTB200_Y_REAL, (float2*)align_ptr(workspace),
-                             (cudaStream_t)stream);
+    float2* spec;
+    FftWork fw;
+    NF_TRY(spectral_layout(g, workspace, workspace_bytes, &spec, &fw));
+    return do_adjoint_finish(g, (float*)grid, (float*)y, flags & NFFTB200_Y_REAL, spec, fw, (cudaStream_t)stream);
 }
 
 int nfftb200_forward_begin(const void* xhat, void* grid, int d, int64_t N, int m, int64_t B, int64_t C, int flags,
@@ -843,9 +1090,11 @@ int nfftb200_forward_begin(const void* xhat, void* grid, int d, int64_t N, int m
     const bool yr = flags & NFFTB200_Y_REAL;
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, !yr, 0));
-    if (workspace_bytes < half_bytes(g) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
-    return do_forward_begin(g, (const float*)xhat, !(flags & NFFTB200_X_COMPLEX), yr, (float*)grid,
-                            (float2*)align_ptr(workspace), (cudaStream_t)stream);
+    float2* spec;
+    FftWork fw;
+    NF_TRY(spectral_layout(g, workspace, workspace_bytes, &spec, &fw));
+    return do_forward_begin(g, (const float*)xhat, !(flags & NFFTB200_X_COMPLEX), yr, (float*)grid, spec, fw,
+                            (cudaStream_t)stream);
 }
 
 int nfftb200_fastsum_middle(void* grid, const void* coeffs, int d, int64_t N, int m, int64_t B, int64_t C, int flags,
@@ -853,9 +1102,11 @@ int nfftb200_fastsum_middle(void* grid, const void* coeffs, int d, int64_t N, in
     NF_REQUIRE(grid && coeffs && workspace, "nfftb200_fastsum_middle: null pointer");
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, 0));
-    if (workspace_bytes < half_bytes(g) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
-    return do_fastsum_middle(g, (float*)grid, (const float*)coeffs, !(flags & NFFTB200_COEFFS_COMPLEX),
-                             (float2*)align_ptr(workspace), (cudaStream_t)stream);
+    float2* spec;
+    FftWork fw;
+    NF_TRY(spectral_layout(g, workspace, workspace_bytes, &spec, &fw));
+    return do_fastsum_middle(g, (float*)grid, (const float*)coeffs, !(flags & NFFTB200_COEFFS_COMPLEX), spec, fw,
+                             (cudaStream_t)stream);
 }
 
 int nfftb200_sort_points(const float* pos, const int64_t* batch, uint32_t* keys_out, uint32_t* perm_out,
@@ -863,14 +1114,16 @@ int nfftb200_sort_points(const float* pos, const int64_t* batch, uint32_t* keys_
                          void* workspace, size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n >= 0 && workspace && (n == 0 || (pos && keys_out && perm_out)), "nfftb200_sort_points: null pointer");
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    if (workspace_bytes < align_up(sort_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
+    Workspace w;
+    NF_TRY(op_layout(NFFTB200_OP_SORT, n, 0, d, N, m, B, C, flags & ~NFFTB200_PLANNED, &g, &w));
+    NF_CHECK_WS(w, workspace_bytes);
     if (tile_out_host) {
         for (int s = 0; s < 3; ++s) tile_out_host[s] = g.T[s];
     }
     SortPlan sp{};
     cudaStream_t st = (cudaStream_t)stream;
-    NF_TRY(sort_points(pos, batch, n, g, align_ptr(workspace), &sp, st));
+    char* ws = align_ptr(workspace);
+    NF_TRY(do_sort(g, pos, batch, flags & NFFTB200_BATCH_OFFSETS, n, ws + w.scratch, ws + w.plan_a, &sp, st));
     if (n > 0) {
         NF_CUDA(cudaMemcpyAsync(keys_out, sp.keys, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
         NF_CUDA(cudaMemcpyAsync(perm_out, sp.perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));

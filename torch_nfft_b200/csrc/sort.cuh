@@ -7,7 +7,7 @@
 // The cell rule is the reference's: cell_a = (int)floorf(pos_a * M)  (:50).  Keys are sorted
 // with a stable LSD radix sort (8-bit digits, per-block digit histograms -> exclusive scan ->
 // in-order scatter), so the permutation is a pure function of the keys: bit-reproducible and
-// equal to numpy's argsort(kind="stable") (tests/test_sort.py).
+// equal to numpy's argsort(kind="stable") (tests/test_parity_gpu.py::test_binning_is_bit_exact).
 #pragma once
 #include "common.cuh"
 
@@ -167,9 +167,28 @@ __device__ __forceinline__ KeyFast key_fast(const Geom& g) {
     return f;
 }
 
-__device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, const int64_t* __restrict__ batch,
+// The batch entry of point i: from the per-point vector batch[n] (the reference's layout, README.md:42-46) or,
+// with nfftb200's NFFTB200_BATCH_OFFSETS, from the B + 1 ascending offsets of the (sorted) point sets.
+struct BatchRef {
+    const int64_t* data;  // nullptr: one point set
+    int offsets;          // 0: data[i] is the entry of point i;  B > 0: data[0..B] are offsets
+};
+
+__device__ __forceinline__ long long batch_of(const BatchRef& br, long long i) {
+    if (!br.data) return 0;
+    if (!br.offsets) return br.data[i];
+    int lo = 0, hi = br.offsets;  // largest b with data[b] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(br.data + mid) <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, const BatchRef& batch,
                                               long long i, const Geom& g, const KeyFast& f) {
-    long long b = batch ? batch[i] : 0;
+    long long b = batch_of(batch, i);
     b = b < 0 ? 0 : (b >= g.B ? g.B - 1 : b);
     uint32_t key = (uint32_t)b;
     const float Mf = (float)g.M;
@@ -187,7 +206,7 @@ __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, con
 }
 
 __global__ void __launch_bounds__(256)
-key_hist_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, long long n, Geom g,
+key_hist_kernel(const float* __restrict__ pos, const BatchRef batch, long long n, Geom g,
                 uint32_t* __restrict__ keys, uint32_t* __restrict__ bin_count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -245,7 +264,7 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uin
 // Keys of one radix tile and, in the same pass, the tile's row of the first radix pass's digit table
 // (saves re-reading the keys in radix_hist_kernel).
 __global__ void __launch_bounds__(kRsThreads)
-key_tile_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, long long n, Geom g,
+key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n, Geom g,
                 uint32_t* __restrict__ keys, uint32_t* __restrict__ table, int nblocks) {
     __shared__ uint32_t hist[kRsBins];
     hist[threadIdx.x] = 0;
@@ -379,17 +398,45 @@ fill_items_kernel(const uint32_t* __restrict__ bin_start, const uint32_t* __rest
 }
 
 // ------------------------------------------------------------------------- host orchestration
-struct SortLayout {
-    size_t keys0, keysA, keysB, idxA, idxB, bin_count, bin_start, nch, chunk_start, items, table, scan, total;
-    long long nbins, max_items, nblocks;
+// The binning result that the window kernels read ("point plan", persistent) and the scratch the sort
+// needs while it runs (transient) are separate regions, so that a caller can keep the plan of a point
+// set (NfftPlan in nfft.py: 4 bytes per point + the bin / work-item tables) and drop the 16 bytes per
+// point of sort scratch.
+struct PlanLayout {   // persistent: perm | bin_start | chunk_start | items | flags
+    size_t perm, bin_start, chunk_start, items, flags, total;
+    long long nbins, max_items;
 };
+struct SortLayout {   // transient scratch
+    size_t keys0, keysA, keysB, idxT, bin_count, nch, table, scan, total;
+    long long nblocks;
+};
+constexpr int kPlanFlagWords = 8;  // flags[0]: points dropped by a window kernel (stale plan), see PlanFlags
+
+inline PlanLayout plan_layout(long long n, const Geom& g) {
+    PlanLayout L{};
+    L.nbins = (long long)g.B * g.tiles_per_batch;
+    L.max_items = n / g.pmax + (L.nbins < n ? L.nbins : n) + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes);
+        return o;
+    };
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    L.perm = take(nn * 4);
+    L.bin_start = take((size_t)(L.nbins + 1) * 4);
+    L.chunk_start = take((size_t)(L.nbins + 1) * 4);
+    L.items = take((size_t)L.max_items * sizeof(uint4));
+    L.flags = take(kPlanFlagWords * 4);
+    L.total = off;
+    return L;
+}
 
 inline SortLayout sort_layout(long long n, const Geom& g) {
     SortLayout L{};
-    L.nbins = (long long)g.B * g.tiles_per_batch;
+    const long long nbins = (long long)g.B * g.tiles_per_batch;
     L.nblocks = (n + kRsTile - 1) / kRsTile;
     if (L.nblocks < 1) L.nblocks = 1;
-    L.max_items = n / g.pmax + (L.nbins < n ? L.nbins : n) + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -400,67 +447,70 @@ inline SortLayout sort_layout(long long n, const Geom& g) {
     L.keys0 = take(nn * 4);
     L.keysA = take(nn * 4);
     L.keysB = take(nn * 4);
-    L.idxA = take(nn * 4);
-    L.idxB = take(nn * 4);
-    L.bin_count = take((size_t)(L.nbins + 1) * 4);
-    L.bin_start = take((size_t)(L.nbins + 1) * 4);
-    L.nch = take((size_t)(L.nbins + 1) * 4);
-    L.chunk_start = take((size_t)(L.nbins + 1) * 4);
-    L.items = take((size_t)L.max_items * sizeof(uint4));
+    L.idxT = take(nn * 4);
+    L.bin_count = take((size_t)(nbins + 1) * 4);
+    L.nch = take((size_t)(nbins + 1) * 4);
     L.table = take((size_t)(kRsBins * L.nblocks + 1) * 4);
-    size_t s1 = scan_scratch_bytes(L.nbins + 1);
+    size_t s1 = scan_scratch_bytes(nbins + 1);
     size_t s2 = scan_scratch_bytes(kRsBins * L.nblocks + 1);
     L.scan = take(s1 > s2 ? s1 : s2);
     L.total = off;
     return L;
 }
 
-// Pointers of the sort result inside `ws` (a pure function of n and the geometry, so a caller that
-// kept the workspace can reuse a previous sort of the same points: NFFTB200_PRESORTED).
-inline void sort_plan_pointers(long long n, const Geom& g, char* ws, SortPlan* plan) {
-    const SortLayout L = sort_layout(n, g);
+inline int sort_passes(const Geom& g) {
+    const long long nbins = (long long)g.B * g.tiles_per_batch;
     int bits = 0;
-    while (bits < 32 && (1ll << bits) < L.nbins) ++bits;
-    const int passes = (bits + 7) / 8;
-    uint32_t* ibuf[2] = {(uint32_t*)(ws + L.idxA), (uint32_t*)(ws + L.idxB)};
-    plan->keys = (uint32_t*)(ws + L.keys0);
-    plan->perm = passes == 0 ? ibuf[0] : ibuf[(passes - 1) & 1];
-    plan->bin_start = (uint32_t*)(ws + L.bin_start);
-    plan->chunk_start = (uint32_t*)(ws + L.chunk_start);
-    plan->items = (uint4*)(ws + L.items);
+    while (bits < 32 && (1ll << bits) < nbins) ++bits;
+    return (bits + 7) / 8;
+}
+
+// Pointers of a point plan inside its persistent region (a pure function of n and the geometry).
+inline void sort_plan_pointers(long long n, const Geom& g, char* plan_mem, SortPlan* plan) {
+    const PlanLayout L = plan_layout(n, g);
+    plan->keys = nullptr;
+    plan->perm = (uint32_t*)(plan_mem + L.perm);
+    plan->bin_start = (uint32_t*)(plan_mem + L.bin_start);
+    plan->chunk_start = (uint32_t*)(plan_mem + L.chunk_start);
+    plan->items = (uint4*)(plan_mem + L.items);
+    plan->flags = (uint32_t*)(plan_mem + L.flags);
     plan->nbins = L.nbins;
     plan->max_items = L.max_items;
 }
 
-// Bins n points; on return plan.* point into `ws` (which must hold sort_layout(n,g).total bytes).
-inline int sort_points(const float* pos, const int64_t* batch, long long n, const Geom& g, char* ws,
-                       SortPlan* plan, cudaStream_t st) {
+// Bins n points: the plan is written to `plan_mem` (plan_layout(n,g).total bytes), `scratch` must hold
+// sort_layout(n,g).total bytes and is dead afterwards (plan->keys points into it: the unsorted tile keys).
+inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_offsets, long long n, const Geom& g,
+                       char* scratch, char* plan_mem, SortPlan* plan, cudaStream_t st) {
     const SortLayout L = sort_layout(n, g);
-    sort_plan_pointers(n, g, ws, plan);
-    uint32_t* keys0 = plan->keys;
-    uint32_t* kbuf[2] = {(uint32_t*)(ws + L.keysA), (uint32_t*)(ws + L.keysB)};
-    uint32_t* ibuf[2] = {(uint32_t*)(ws + L.idxA), (uint32_t*)(ws + L.idxB)};
-    uint32_t* bin_count = (uint32_t*)(ws + L.bin_count);
+    sort_plan_pointers(n, g, plan_mem, plan);
+    const long long nbins = plan->nbins;
+    uint32_t* keys0 = (uint32_t*)(scratch + L.keys0);
+    plan->keys = keys0;
+    const int passes = sort_passes(g);
+    // the last radix pass writes its permutation straight into the plan
+    uint32_t* kbuf[2] = {(uint32_t*)(scratch + L.keysA), (uint32_t*)(scratch + L.keysB)};
+    uint32_t* ibuf[2] = {(uint32_t*)(scratch + L.idxT), (uint32_t*)(scratch + L.idxT)};
+    ibuf[passes == 0 ? 0 : ((passes - 1) & 1)] = plan->perm;
+    uint32_t* bin_count = (uint32_t*)(scratch + L.bin_count);
     uint32_t* bin_start = plan->bin_start;
-    uint32_t* nch = (uint32_t*)(ws + L.nch);
+    uint32_t* nch = (uint32_t*)(scratch + L.nch);
     uint32_t* chunk_start = plan->chunk_start;
-    uint32_t* table = (uint32_t*)(ws + L.table);
-    uint32_t* scan = (uint32_t*)(ws + L.scan);
+    uint32_t* table = (uint32_t*)(scratch + L.table);
+    uint32_t* scan = (uint32_t*)(scratch + L.scan);
+    const BatchRef bref{batch, batch_is_offsets ? g.B : 0};
 
-    int bits = 0;
-    while (bits < 32 && (1ll << bits) < L.nbins) ++bits;
-    const int passes = (bits + 7) / 8;
-
-    NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(L.nbins + 1) * 4, st));
+    NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, st));
+    NF_CUDA(cudaMemsetAsync(plan->flags, 0, kPlanFlagWords * 4, st));
     // stable LSD radix sort of (key, index) over the key bits that can be set
     const uint32_t* kin = keys0;
     const uint32_t* iin = nullptr;  // identity payload on the first pass
     if (n > 0) {
         if (passes == 0) {
-            NF_LAUNCH(key_hist_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pos, batch, n, g, keys0, bin_count);
-            NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, ibuf[0], n);
+            NF_LAUNCH(key_hist_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pos, bref, n, g, keys0, bin_count);
+            NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, plan->perm, n);
         } else {
-            NF_LAUNCH(key_tile_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, pos, batch, n, g, keys0, table,
+            NF_LAUNCH(key_tile_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, pos, bref, n, g, keys0, table,
                       (int)L.nblocks);
         }
         for (int p = 0; p < passes; ++p) {
@@ -481,11 +531,11 @@ inline int sort_points(const float* pos, const int64_t* batch, long long n, cons
         }
     }
     // bin offsets, chunks of at most pmax points, work items
-    NF_TRY(scan_exclusive(bin_count, bin_start, L.nbins, scan, st));
-    NF_LAUNCH(chunk_count_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, bin_start, L.nbins, g.pmax, nch);
-    NF_TRY(scan_exclusive(nch, chunk_start, L.nbins, scan, st));
-    NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)L.max_items * sizeof(uint4), st));
-    NF_LAUNCH(fill_items_kernel, (unsigned)((L.nbins + 255) / 256), 256, 0, st, bin_start, chunk_start, L.nbins,
+    NF_TRY(scan_exclusive(bin_count, bin_start, nbins, scan, st));
+    NF_LAUNCH(chunk_count_kernel, (unsigned)((nbins + 255) / 256), 256, 0, st, bin_start, nbins, g.pmax, nch);
+    NF_TRY(scan_exclusive(nch, chunk_start, nbins, scan, st));
+    NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)plan->max_items * sizeof(uint4), st));
+    NF_LAUNCH(fill_items_kernel, (unsigned)((nbins + 255) / 256), 256, 0, st, bin_start, chunk_start, nbins,
               plan->items);
     return NFFTB200_OK;
 }

@@ -35,7 +35,13 @@ struct WindowArgs {
     const uint4* items;
     long long nbins;
     int k0;                  // first component handled by this pass
+    uint32_t* flags;         // point plan flags: flags[0] counts points found outside their tile (stale plan)
 };
+
+// a point of a work item lies outside the item's tile: the plan was made for other positions
+__device__ __forceinline__ void note_dropped_point(const WindowArgs& a) {
+    if (a.flags) atomicAdd(a.flags, 1u);
+}
 
 __device__ __forceinline__ int fast_div(int x, int d, float inv) {
     int q = (int)((float)x * inv);
@@ -76,8 +82,8 @@ __device__ __forceinline__ void stage_prefetch(StageRegs<DIM>& r, const WindowAr
 }
 
 template <int DIM, int LC>
-__device__ __forceinline__ void stage_store(const StageRegs<DIM>& r, const Geom& g, int cnt, const int* tile_org,
-                                            float* s_psi, int* s_rec, bool store_index) {
+__device__ __forceinline__ void stage_store(const StageRegs<DIM>& r, const Geom& g, const WindowArgs& a, int cnt,
+                                            const int* tile_org, float* s_psi, int* s_rec, bool store_index) {
     const int L = LC ? LC : g.L, LP = g.LP;
 #pragma unroll
     for (int k = 0; k < StageRegs<DIM>::kItems; ++k) {
@@ -102,7 +108,13 @@ __device__ __forceinline__ void stage_store(const StageRegs<DIM>& r, const Geom&
                 }
             }
             // first tap in padded-tile coordinates: wrapped cell - m - (tile origin)
-            const int s0 = wrap_mod(c, g.M) - g.m - tile_org[slot];
+            int s0 = wrap_mod(c, g.M) - g.m - tile_org[slot];
+            if (s0 < 0 || s0 > g.P[slot] - L) {
+                // only a stale plan (positions changed after the binning) gets here: stay inside the tile
+                // and report it through the plan's flag word instead of writing out of bounds
+                s0 = s0 < 0 ? 0 : g.P[slot] - L;
+                note_dropped_point(a);
+            }
             s_rec[q * 4 + slot] = s0 | ((s0 % L) << 16);
             if (slot == 0) {
                 if (DIM < 3) s_rec[q * 4 + 2] = 0;
@@ -324,7 +336,7 @@ spread_kernel(const Geom g, const WindowArgs a) {
 
     for (long long p0 = t.p_lo; p0 < t.p_hi; p0 += kSubBatch) {
         const int cnt = (int)((t.p_hi - p0) < kSubBatch ? (t.p_hi - p0) : kSubBatch);
-        stage_store<DIM, LC>(regs, g, cnt, s_org, s_psi, s_rec, false);
+        stage_store<DIM, LC>(regs, g, a, cnt, s_org, s_psi, s_rec, false);
 #pragma unroll
         for (int k = 0; k < kXItems; ++k) {
             const int w = tid + k * blockDim.x;
@@ -460,7 +472,7 @@ gather_kernel(const Geom g, const WindowArgs a) {
 
     for (long long p0 = t.p_lo; p0 < t.p_hi; p0 += kSubBatch) {
         const int cnt = (int)((t.p_hi - p0) < kSubBatch ? (t.p_hi - p0) : kSubBatch);
-        stage_store<DIM, LC>(regs, g, cnt, s_org, s_psi, s_rec, true);
+        stage_store<DIM, LC>(regs, g, a, cnt, s_org, s_psi, s_rec, true);
         __syncthreads();
         {
             const long long left = t.p_hi - (p0 + kSubBatch);

@@ -77,6 +77,8 @@ spread1d_kernel(const Geom g, const WindowArgs a) {
             if (c >= 0 && c < T) {  // anything else can only come from a stale / foreign sort
                 cell[k] = c;
                 atomicAdd(&s_cur[c], 1);
+            } else {
+                note_dropped_point(a);
             }
         }
     }
@@ -169,6 +171,7 @@ gather1d_kernel(const Geom g, const WindowArgs a) {
         float acc[NCOMP];
 #pragma unroll
         for (int k = 0; k < NCOMP; ++k) acc[k] = 0.f;
+        if (c < 0 || c >= g.T[0]) note_dropped_point(a);  // stale / foreign plan
         if (c >= 0 && c < g.T[0]) {
             const float* row = tile + c + shift;
             for (int l = 0; l < g.L; ++l) {

@@ -135,12 +135,22 @@ __device__ __forceinline__ float window_exp(float x) {
 #ifndef NFFT_REG_LOCK_NS
 #define NFFT_REG_LOCK_NS 32
 #endif
+#ifndef NFFT_REG_LOCK_EXCH
+#define NFFT_REG_LOCK_EXCH 0
+#endif
+// Experiment: warp w of a CTA starts its sweep w * NFFT_REG_STAGGER_NS later, so that the warps (which all start
+// at the bottom of their columns after the same barrier) do not meet at the same plane-pair lock.
+#ifndef NFFT_REG_STAGGER_NS
+#define NFFT_REG_STAGGER_NS 0
+#endif
 __device__ __forceinline__ void lock_acquire(int* lk) {
 #if NFFT_REG_LOCK_TTAS
     for (;;) {
         if (*reinterpret_cast<volatile int*>(lk) == 0 && atomicCAS(lk, 0, 1) == 0) break;
         __nanosleep(NFFT_REG_LOCK_NS);
     }
+#elif NFFT_REG_LOCK_EXCH
+    while (atomicExch(lk, 1) != 0) __nanosleep(NFFT_REG_LOCK_NS);  // ATOMS.EXCH instead of the CAS form
 #else
     while (atomicCAS(lk, 0, 1) != 0) __nanosleep(NFFT_REG_LOCK_NS);
 #endif
@@ -304,11 +314,13 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
             const int cy = wrap_mod((int)floorf(p1 * Mf), g.M) - lo1;
             const int cx = wrap_mod((int)floorf(p2 * Mf), g.M) - lo0;
             const int bx = cx / SX, by = cy / SY, bz = cz / SZ;
-            // a point outside its tile can only come from a stale / foreign sort: drop it rather
-            // than index shared memory out of bounds
+            // a point outside its tile can only come from a stale / foreign plan: drop it rather
+            // than index shared memory out of bounds, and count it in the plan's flag word
             if (cx >= 0 && cy >= 0 && cz >= 0 && bx < nsx && by < nsy && bz < nsz) {
                 sc[k] = ((by * nsx + bx) * nsz + bz) | ((cx - bx * SX) | (cy - by * SY) << 2 | (cz - bz * SZ) << 4) << 24;
                 atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
+            } else {
+                note_dropped_point(a);
             }
         }
     }
@@ -540,6 +552,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 
     // work units (columns of supercells or z-ranges of heavy columns) are handed out dynamically
     const int nunits = s_nunits;
+#if NFFT_REG_STAGGER_NS > 0
+    if (warp > 0) __nanosleep(warp * NFFT_REG_STAGGER_NS);
+#endif
     for (;;) {
         int col = 0;
         if (lane == 0) col = atomicAdd(&s_next, 1);

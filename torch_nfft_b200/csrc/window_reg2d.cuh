@@ -69,6 +69,8 @@ __device__ __forceinline__ void bucket_points_2d(const Geom& g, const WindowArgs
             if (cx >= 0 && cy >= 0 && bx < nsx && by < nsy) {
                 sc[k] = (by * nsx + bx) | ((cx - bx * kReg2S) | (cy - by * kReg2S) << 2) << 24;
                 atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
+            } else {
+                note_dropped_point(a);
             }
         }
     }

@@ -60,7 +60,7 @@ class CudaEngine:
 
     @staticmethod
     def _geom(pos, batch, batch_size):
-        pos, batch, n, d, B = _nfft._check_points(pos, batch, batch_size)
+        pos, batch, n, d, B, _ = _nfft._check_points(pos, batch, batch_size)
         return pos, batch, n, d, B
 
     def spread(self, x, pos, batch, B, N, m):
@@ -73,8 +73,8 @@ class CudaEngine:
         L = _lib.lib()
         with torch.cuda.device(pos.device):
             ws = _nfft._workspace(L.nfftb200_workspace_bytes(_lib.OP_SPREAD, n, 0, d, N, m, B, C, flags), pos.device)
-            _lib.check(L.nfftb200_spread(pos.data_ptr(), x.data_ptr(), _nfft._ptr(batch), grid.data_ptr(), n, d, N, m,
-                                         B, C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(pos.device)),
+            _lib.check(L.nfftb200_spread(pos.data_ptr(), x.data_ptr(), _nfft._ptr(batch), 0, 0, grid.data_ptr(), n, d, N,
+                                         m, B, C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(pos.device)),
                        "spread")
         return grid
 
@@ -114,8 +114,8 @@ class CudaEngine:
         L = _lib.lib()
         with torch.cuda.device(grid.device):
             ws = _nfft._workspace(L.nfftb200_workspace_bytes(_lib.OP_GATHER, 0, n, d, N, m, B, C, flags), grid.device)
-            _lib.check(L.nfftb200_gather(pos.data_ptr(), _nfft._ptr(batch), grid.data_ptr(), y.data_ptr(), n, d, N, m, B,
-                                         C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(grid.device)), "gather")
+            _lib.check(L.nfftb200_gather(pos.data_ptr(), _nfft._ptr(batch), 0, 0, grid.data_ptr(), y.data_ptr(), n, d, N, m,
+                                         B, C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(grid.device)), "gather")
         return y
 
     def fastsum_middle(self, grid, coeffs, d, B, N, m):

@@ -17,15 +17,22 @@ adjoint+forward pair) runs in 0.12 ms per pair replayed against 0.21 ms launched
     y, f = g.replay()                                    # the tensors returned at capture time, refilled
 
 Rules (those of CUDA graphs): the captured function must not synchronise with the host, so pass
-`batch_size=` (otherwise `batch[-1].item()` is read, reference core_cuda.cu:60); shapes, dtypes and
-tensor addresses are frozen; the points are binned again on the device in every replay.
+`batch_size=` or `batch_ptr=` (otherwise `batch[-1].item()` is read, reference core_cuda.cu:60); shapes,
+dtypes and tensor addresses are frozen.  Points are binned inside the captured function -- by the
+transforms themselves or by an `NfftPlan` created inside it -- so every replay bins the positions it
+finds in the tensors; a plan made OUTSIDE the function is baked in and only valid while `pos` is unchanged.
+
+cuFFT: the captured FFT kernels take their work area from the capture stream's workspace (kept alive by
+this object) and reference the twiddle tables of the cached cuFFT handles, so the plan cache is pinned
+(`nfftb200_plan_cache_pin`) until `close()`: `clear_caches()` keeps the handles and warns meanwhile.
 """
 from __future__ import annotations
 
 import torch
 
 from . import _lib
-from .nfft import forget_sorted_points, release_stream_workspace
+from . import nfft as _nfft
+from .nfft import release_stream_workspace
 
 
 class GraphedTransforms:
@@ -47,13 +54,14 @@ class GraphedTransforms:
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
-            # the capture must not inherit a sort remembered from the warm-up: every replay bins the
-            # points it finds in the tensors
-            forget_sorted_points()
+            _lib.lib().nfftb200_plan_cache_pin(1)
+            self._pinned = True
             with torch.cuda.graph(self.graph, stream=self._stream):
                 self.outputs = fn()
             self.kernels_per_replay = _lib.launch_count() - before
-            forget_sorted_points()  # a replay may change what the capture stream's workspace holds
+            # the captured kernels hold raw pointers into the capture stream's workspace: keep it alive even if
+            # the cache entry is replaced
+            self._workspace = _nfft._workspaces.get((self.device.index, self._stream.cuda_stream))
 
     def replay(self):
         """Runs the captured transforms on the current stream; returns the output tensors of the capture."""
@@ -69,6 +77,10 @@ class GraphedTransforms:
         torch.cuda.synchronize(self.device)  # replays still in flight use the workspace
         self.graph = None
         self.outputs = None
+        self._workspace = None
+        if getattr(self, "_pinned", False):
+            _lib.lib().nfftb200_plan_cache_pin(-1)
+            self._pinned = False
         release_stream_workspace(self.device.index, self._stream.cuda_stream)
 
     def __del__(self):

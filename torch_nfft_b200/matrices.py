@@ -8,7 +8,7 @@ import warnings
 
 import torch
 
-from .nfft import nfft_fastsum
+from .nfft import NfftPlan, nfft_fastsum
 
 
 class AbstractMatrix:
@@ -58,10 +58,22 @@ class GramMatrix(AbstractMatrix):
         self.coeffs, self.cutoff = coeffs, cutoff
         self.sources, self.targets = sources, targets
         self.source_batch, self.target_batch = source_batch, target_batch
+        # the points of a matrix are fixed: they are binned by the first product and never again (the reference
+        # recomputes its per-point scratch in every product, core_cuda.cu:188-211); CPU tensors raise in apply
+        self._plans = None
+
+    def _point_plans(self):
+        if self._plans is None:
+            src = NfftPlan(self.sources, self.source_batch)
+            same = self.sources is self.targets and self.source_batch is self.target_batch
+            self._plans = (src, src if same else NfftPlan(self.targets, self.target_batch, batch_size=src.batch_size))
+        return self._plans
 
     def apply(self, x):
+        source_plan, target_plan = self._point_plans()
         return nfft_fastsum(x, self.coeffs, self.sources, self.targets, self.source_batch, self.target_batch,
-                            cutoff=self.cutoff)
+                            cutoff=self.cutoff, batch_size=source_plan.batch_size, source_plan=source_plan,
+                            target_plan=target_plan)
 
     def is_symmetric(self):
         return self.sources is self.targets and self.source_batch is self.target_batch
@@ -69,8 +81,11 @@ class GramMatrix(AbstractMatrix):
     def transpose(self):
         if self.is_symmetric():
             return self
-        return GramMatrix(self.coeffs, self.targets, self.sources, self.target_batch, self.source_batch,
-                          cutoff=self.cutoff)
+        flipped = GramMatrix(self.coeffs, self.targets, self.sources, self.target_batch, self.source_batch,
+                             cutoff=self.cutoff)
+        if self._plans is not None:  # the same binnings serve the transposed product
+            flipped._plans = (self._plans[1], self._plans[0])
+        return flipped
 
 
 def _col(v, x):
