@@ -162,15 +162,16 @@ int nfftb200_fastsum_middle(void* grid, const void* coeffs, int d, int64_t N, in
                             int64_t C, int flags, void* workspace, size_t workspace_bytes,
                             void* stream);
 
-/* Deterministic binning only: keys_out[n] (uint32 tile key per point, input order),
- * perm_out[n] (uint32 stable sort permutation), tile_out[3] (tile extents X,Y,Z used). */
+/* Deterministic binning only: keys_out[n] (uint32 sort key per point, input order: tile key <<
+ * fine_bits | position of the point's supercell inside the tile, see debug_geometry), perm_out[n]
+ * (uint32 stable sort permutation by that key), tile_out[3] (tile extents X,Y,Z used). */
 int nfftb200_sort_points(const float* pos, const int64_t* batch, uint32_t* keys_out,
                          uint32_t* perm_out, int32_t* tile_out_host, int64_t n, int d, int64_t N,
                          int m, int64_t B, int64_t C, int flags, void* workspace,
                          size_t workspace_bytes, void* stream);
 
-/* Host-only: the tiling the engine would use.  out[21] = dim,N,M,m,L, T[3], nt[3], P[3], sY, sZ,
- * tile_elems, ncomp, pmax, spread_threads, use_reg (slot order X,Y,Z). */
+/* Host-only: the tiling the engine would use.  out[22] = dim,N,M,m,L, T[3], nt[3], P[3], sY, sZ,
+ * tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits (slot order X,Y,Z). */
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n,
                             int32_t* out);
 

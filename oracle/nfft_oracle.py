@@ -419,6 +419,24 @@ def tile_keys(pos, batch, N, tile):
     return key.astype(np.int64)
 
 
+def sort_keys(pos, batch, N, tile, fine_bits=0, supercell=(2, 4, 4)):
+    """The engine's full sort key: tile key << fine_bits | top fine_bits bits of the 7-bit hierarchical index
+    [y half | x half | y quarter | x quarter | z supercell] of the point's supercell inside its 16^3 tile
+    (the engine's own binning rule, torch_nfft_b200/csrc/sort.cuh: fine_index; 3D only).
+    `tile` / `supercell` are in API dimension order (dim 0 = slot Z ... dim 2 = slot X)."""
+    key = tile_keys(pos, batch, N, tile)
+    if fine_bits == 0:
+        return key
+    pos32, _, _ = _as_points(pos, batch)
+    assert pos32.shape[1] == 3
+    M = 2 * N
+    cw = np.mod(compute_cells(pos32, M), M)
+    inside = cw - (cw // np.asarray(tile)) * np.asarray(tile)
+    bz, by, bx = (inside[:, a] // supercell[a] for a in range(3))
+    fine = ((by >> 1) << 6) | ((bx >> 1) << 5) | ((by & 1) << 4) | ((bx & 1) << 3) | bz
+    return ((key << fine_bits) | (fine >> (7 - fine_bits))).astype(np.int64)
+
+
 def stable_permutation(keys):
     """Stable sort permutation: what the engine's counting sort must reproduce bit-for-bit."""
     return np.argsort(keys, kind="stable").astype(np.int64)

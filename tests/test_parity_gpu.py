@@ -136,7 +136,9 @@ def test_engine_matches_reference_golden(fname):
 # ---------------------------------------------------------------------------------------------
 # integer work: bit-exact
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("d,N,m,B,n", [(1, 1024, 8, 5, 3000), (2, 256, 4, 3, 20000), (3, 128, 4, 2, 150000), (3, 16, 3, 2, 999), (2, 64, 3, 300, 50)])
+@pytest.mark.parametrize("d,N,m,B,n", [(1, 1024, 8, 5, 3000), (2, 256, 4, 3, 20000), (3, 128, 4, 2, 150000), (3, 16, 3, 2, 999), (2, 64, 3, 300, 50),
+                                       (3, 16, 4, 1, 40000),   # dense (> 1 point per cell): all 7 fine key bits
+                                       (3, 64, 4, 1, 3000)])   # 9 tile bits: 7 spare bits in the second radix pass
 def test_binning_is_bit_exact(d, N, m, B, n):
     rng = np.random.default_rng(d + N)
     pos, batch = make_points(rng, d, B, n, ragged=True)
@@ -154,7 +156,8 @@ def test_binning_is_bit_exact(d, N, m, B, n):
                                           ctypes.cast(tile, ctypes.c_void_p), nn, d, N, m, B, 1, 0, ws.data_ptr(),
                                           ws.numel(), torch.cuda.current_stream().cuda_stream), "sort")
         torch.cuda.synchronize()
-        okeys = O.tile_keys(pos, batch, N, list(tile)[:d][::-1])
+        fine = _lib.geometry(d, N, m, B, 1, 0, nn)["fine_bits"]
+        okeys = O.sort_keys(pos, batch, N, list(tile)[:d][::-1], fine)
         assert np.array_equal(keys.cpu().numpy().astype(np.int64), okeys)
         assert np.array_equal(perm.cpu().numpy().astype(np.int64), O.stable_permutation(okeys))
 

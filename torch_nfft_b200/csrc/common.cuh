@@ -84,6 +84,8 @@ struct Geom {
     int pmax;            // max points per work item
     int spread_threads;  // block size of the spread kernel
     int use_reg;         // 1: register-stencil kernels (window_reg.cuh), 0: team kernels (window.cuh)
+    int fine_bits;       // low bits of a sort key: position of the point's supercell inside its tile (sort.cuh)
+    int sc[3];           // supercell extent per slot the fine bits refer to
     float inv_b, inv_sqrt_b_pi, c_hat;
 };
 

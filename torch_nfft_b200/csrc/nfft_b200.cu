@@ -14,6 +14,7 @@
 #include "window1d.cuh"
 #include <nvtx3/nvToolsExt.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <initializer_list>
 #include <map>
@@ -117,6 +118,13 @@ static void choose_strides(Geom& g) {
     g.sY = g.P[0];
     g.sZ = g.P[0] * g.P[1];
     if (g.dim == 1) return;
+    if (g.use_reg == 1) {
+        // 3D register-stencil kernels: rows dense (a TMA box plane is P0 x P1 floats, row pitch P0), planes
+        // 128-byte aligned (TMA shared-memory address).  Bank conflicts of the sweep's (x, y)-position accesses
+        // are the same for sY = 28 as for the previous 29 (1.83 wavefronts per access at L = 10).
+        g.sZ = (g.P[0] * g.P[1] + 31) / 32 * 32;
+        return;
+    }
     std::lock_guard<std::mutex> lock(g_stride_mutex);
     const StrideKey key{g.dim, g.L, g.P[0], g.P[1], g.P[2]};
     auto it = g_strides.find(key);
@@ -231,6 +239,26 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     g.tiles_per_batch = g.nt[0] * g.nt[1] * g.nt[2];
     if ((long long)g.tiles_per_batch * B >= (1ll << 31)) NF_FAIL(NFFTB200_ERR_INVALID, "too many tiles");
 
+    // Fine sort-key bits (sort.cuh: fine_index): only for the 3D register-stencil tiling with full 16^3 tiles of
+    // 4 x 4 x 2 supercells.  The bits that fit the radix passes the tile key needs anyway are free; a dense point
+    // set (>= 1 point per oversampled cell on average: c5) gets all of them even if that adds a pass, because
+    // its tiles are cut into many chunks and the sweep gains far more than the pass costs.
+    g.fine_bits = 0;
+    g.sc[0] = g.sc[1] = g.sc[2] = 1;
+    static const bool no_fine = getenv("NFFTB200_NO_FINE_SORT") != nullptr;
+    if (g.use_reg == 1 && !no_fine && kRegSX == 4 && kRegSY == 4 && kRegSZ == 2 && g.T[0] == 16 && g.T[1] == 16 &&
+        g.T[2] == 16) {
+        g.sc[0] = kRegSX, g.sc[1] = kRegSY, g.sc[2] = kRegSZ;
+        int tile_bits = 0;
+        while ((1ll << tile_bits) < (long long)g.tiles_per_batch * B) ++tile_bits;
+        const int spare = (tile_bits + 7) / 8 * 8 - tile_bits;
+        const bool dense = (double)n_points >= (double)B * (double)g.Md;
+        int k = dense ? kFineBitsMax : (spare < kFineBitsMax ? spare : kFineBitsMax);
+        if (tile_bits == 0 && !dense) k = 0;  // a single tile and few points: no radix pass at all
+        if (k > 31 - tile_bits) k = 31 - tile_bits;
+        g.fine_bits = k < 0 ? 0 : k;
+    }
+
     const int team = d == 1 ? g.L : g.L * g.L;
     choose_strides(g);
     long long te = d == 1 ? g.P[0] : (d == 2 ? (long long)g.sY * g.P[1] : (long long)g.sZ * g.P[2]);
@@ -310,6 +338,53 @@ static int ensure_dynamic_smem(const void* kern, size_t smem) {
     return NFFTB200_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// TMA tensor map of the real oversampled grid (window_reg.cuh).  cuTensorMapEncodeTiled is a driver entry
+// point: it is looked up through the runtime (no link dependency on libcuda).
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static std::mutex mu;
+    static bool looked_up = false;
+    static EncodeTiledFn fn = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!looked_up) {
+        looked_up = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// true (and *map filled) if the 3D register-stencil kernels can move this grid's tile planes by TMA
+static bool make_grid_tensor_map(const Geom& g, float* grid, CUtensorMap* map) {
+    static const bool disabled = getenv("NFFTB200_NO_TMA") != nullptr;
+    memset(map, 0, sizeof(*map));
+    if (disabled || g.use_reg != 1 || g.cplx || g.dim != 3) return false;
+    if (g.P[0] > g.M || g.P[1] > g.M || g.P[2] > g.M) return false;  // tiny grids: a tile wraps more than once
+    if (g.P[0] > 256 || g.P[1] > 256 || (g.P[0] * 4) % 16 != 0 || (g.sZ * 4) % 128 != 0 || g.sY != g.P[0]) return false;
+    if (((uintptr_t)grid & 15) != 0 || (g.M * 4) % 16 != 0) return false;
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t M = (cuuint64_t)g.M;
+    const cuuint64_t dims[4] = {M, M, M, (cuuint64_t)g.B * g.C};
+    const cuuint64_t strides[3] = {M * 4, M * M * 4, M * M * M * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)g.P[0], (cuuint32_t)g.P[1], 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, grid, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+typedef void (*WindowKernelTma)(const Geom, const WindowArgs, const CUtensorMap);
+
 static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPlan& sp, cudaStream_t st) {
     a.perm = sp.perm;
     a.bin_start = sp.bin_start;
@@ -367,7 +442,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
     if (g.use_reg == 1) {
         // supercell kRegSX x kRegSY x kRegSZ = 4 x 4 x 2 cells; for m = 4 the register block is 13 x 13 x 12:
         // 6 positions x 6 float2 accumulators per lane
-        WindowKernel kern = nullptr;
+        WindowKernelTma kern = nullptr;
         int win_floats = 0;
         switch (g.m) {
 #define NF_REG_CASE(M_, L_)                                                                          \
@@ -386,9 +461,11 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         const int nsc = ((g.T[0] + kRegSX - 1) / kRegSX) * ((g.T[1] + kRegSY - 1) / kRegSY) * ((g.T[2] + kRegSZ - 1) / kRegSZ);
         const size_t smem = reg_smem_bytes(g, nsc, win_floats);
         NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
+        CUtensorMap tmap;
+        a.use_tma = make_grid_tensor_map(g, a.grid, &tmap) ? 1 : 0;
         for (int k0 = 0; k0 < g.K; ++k0) {
             a.k0 = k0;
-            NF_LAUNCH(kern, (unsigned)sp.max_items, kRegThreads, smem, st, g, a);
+            NF_LAUNCH(kern, (unsigned)sp.max_items, kRegThreads, smem, st, g, a, tmap);
         }
         return NFFTB200_OK;
     }
@@ -746,13 +823,13 @@ int nfftb200_version(void) { return 200; }
 const char* nfftb200_last_error(void) { return g_err; }
 int64_t nfftb200_launch_count(void) { return (int64_t)g_launches.load(); }
 
-// out[0..20] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads, use_reg
+// out[0..21] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n, int32_t* out) {
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    int v[21] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
-                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg};
-    for (int i = 0; i < 21; ++i) out[i] = v[i];
+    int v[22] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
+                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg, g.fine_bits};
+    for (int i = 0; i < 22; ++i) out[i] = v[i];
     return NFFTB200_OK;
 }
 

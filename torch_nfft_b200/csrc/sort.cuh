@@ -186,6 +186,18 @@ __device__ __forceinline__ long long batch_of(const BatchRef& br, long long i) {
     return lo;
 }
 
+// Fine part of a key (3D register-stencil tiling, 16^3 tiles of 4 x 4 x 2 supercells): the supercell of the
+// point inside its tile as a HIERARCHICAL index, most significant first
+//   [ y half | x half | y quarter | x quarter | z supercell (3 bits) ]
+// of which the top g.fine_bits bits are kept.  Sorting by (tile, fine) makes the chunks a heavy tile is cut
+// into spatially compact -- a quadrant, a supercell column, a z-range of it -- instead of random samples of
+// the whole tile, so the points of a chunk share register blocks in the sweep (window_reg.cuh).
+constexpr int kFineBitsMax = 7;
+__device__ __forceinline__ uint32_t fine_index(int cx, int cy, int cz, const Geom& g) {
+    const int bx = cx / g.sc[0], by = cy / g.sc[1], bz = cz / g.sc[2];  // < 4, < 4, < 8
+    return (uint32_t)(((by >> 1) << 6) | ((bx >> 1) << 5) | ((by & 1) << 4) | ((bx & 1) << 3) | bz);
+}
+
 __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, const BatchRef& batch,
                                               long long i, const Geom& g, const KeyFast& f) {
     long long b = batch_of(batch, i);
@@ -193,15 +205,19 @@ __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, con
     uint32_t key = (uint32_t)b;
     const float Mf = (float)g.M;
     const float* p = pos + i * g.dim;
+    int in_tile[3] = {0, 0, 0};
 #pragma unroll
     for (int slot = 2; slot >= 0; --slot) {
         if (slot < g.dim) {
             const int c = (int)floorf(p[g.dim - 1 - slot] * Mf);  // spatial_window_operations.cu:50
             const int cw = f.m_pow2 ? (c & (g.M - 1)) : wrap_mod(c, g.M);
             const int tile = f.tshift[slot] >= 0 ? (cw >> f.tshift[slot]) : cw / g.T[slot];
+            in_tile[slot] = cw - tile * g.T[slot];
             key = key * (uint32_t)g.nt[slot] + (uint32_t)tile;
         }
     }
+    if (g.fine_bits > 0)
+        key = (key << g.fine_bits) | (fine_index(in_tile[0], in_tile[1], in_tile[2], g) >> (kFineBitsMax - g.fine_bits));
     return key;
 }
 
@@ -212,17 +228,18 @@ key_hist_kernel(const float* __restrict__ pos, const BatchRef batch, long long n
     if (i >= n) return;
     const uint32_t key = point_key(pos, batch, i, g, key_fast(g));
     keys[i] = key;
-    if (bin_count) atomicAdd(&bin_count[key], 1u);  // only when no radix pass follows (single bin)
+    if (bin_count) atomicAdd(&bin_count[key >> g.fine_bits], 1u);  // only when no radix pass follows (single bin)
 }
 
 // Bin sizes from the SORTED keys: one atomicAdd per run of equal keys per warp (a global atomic per
 // point on 2^14 hot addresses costs 0.45 ms at 2^24 points; this is ~30x fewer atomics).
 __global__ void __launch_bounds__(256)
-count_sorted_kernel(const uint32_t* __restrict__ keys_sorted, long long n, uint32_t* __restrict__ bin_count) {
+count_sorted_kernel(const uint32_t* __restrict__ keys_sorted, long long n, int fine_bits,
+                    uint32_t* __restrict__ bin_count) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = i < n;
-    const uint32_t key = valid ? keys_sorted[i] : 0xffffffffu;
+    const uint32_t key = valid ? (keys_sorted[i] >> fine_bits) : 0xffffffffu;  // bin = tile part of the key
     const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool head = valid && (lane == 0 || prev != key);
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
@@ -458,12 +475,13 @@ inline SortLayout sort_layout(long long n, const Geom& g) {
     return L;
 }
 
-inline int sort_passes(const Geom& g) {
+inline int tile_key_bits(const Geom& g) {
     const long long nbins = (long long)g.B * g.tiles_per_batch;
     int bits = 0;
     while (bits < 32 && (1ll << bits) < nbins) ++bits;
-    return (bits + 7) / 8;
+    return bits;
 }
+inline int sort_passes(const Geom& g) { return (tile_key_bits(g) + g.fine_bits + 7) / 8; }
 
 // Pointers of a point plan inside its persistent region (a pure function of n and the geometry).
 inline void sort_plan_pointers(long long n, const Geom& g, char* plan_mem, SortPlan* plan) {
@@ -527,7 +545,7 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
             iin = iout;
         }
         if (passes > 0) {
-            NF_LAUNCH(count_sorted_kernel, (unsigned)((n + 255) / 256), 256, 0, st, kin, n, bin_count);
+            NF_LAUNCH(count_sorted_kernel, (unsigned)((n + 255) / 256), 256, 0, st, kin, n, g.fine_bits, bin_count);
         }
     }
     // bin offsets, chunks of at most pmax points, work items

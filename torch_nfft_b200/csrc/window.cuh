@@ -35,7 +35,9 @@ struct WindowArgs {
     const uint4* items;
     long long nbins;
     int k0;                  // first component handled by this pass
-    uint32_t* flags;         // point plan flags: flags[0] counts points found outside their tile (stale plan)
+    uint32_t* flags;         // point plan flags: flags[0] counts points found outside their tile (stale plan),
+                             // flags[1] TMA transfers that did not complete (must stay 0)
+    int use_tma;             // 3D register-stencil kernels: tile planes move by TMA (window_reg.cuh)
 };
 
 // a point of a work item lies outside the item's tile: the plan was made for other positions

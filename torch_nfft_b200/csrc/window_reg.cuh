@@ -14,9 +14,72 @@
 // (gather); the reference multiplies dimension 0 first (spatial_window_operations.cu:146-156,
 // 257-267).  The difference is a rounding of ~6e-8 per tap, far below the 1e-5 parity budget.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only: the encoder is looked up at run time, nfft_b200.cu)
+
 #include "window.cuh"
 
 namespace nfftb200 {
+
+// ----------------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) on the real oversampled grid, described by ONE rank-4 tensor map per launch:
+//   dims {M, M, M, B*C} (X fastest), box {P0, P1, 1, 1} = one plane of a CTA's padded tile, dense in shared
+//   memory (row pitch P0 floats, planes 128-byte aligned: Geom::sY = P0, sZ = roundup(P0 * P1, 32)).
+// * spread: a finished plane pair of the shared-memory tile is ADDED into the grid by the TMA unit
+//   (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG) as soon as the last warp has added into it, while the
+//   warps go on sweeping: no register staging, no LSU traffic, no flush phase after the sweep.  Out-of-range
+//   box elements are not written, so the periodic wrap is one more box at (x -+ M, y -+ M).
+// * gather: the tile's planes are LOADED by the TMA unit (UTMALDG) into the shared-memory tile, completion on
+//   an mbarrier, while the CTA buckets its points.  Out-of-range elements of a load are zero-FILLED, which
+//   would overwrite the other half of a wrapped plane, so tiles that cross the grid boundary in X or Y (2 of
+//   16 tile rows per dimension at c4) keep the LDGSTS path; the Z wrap is per plane and free.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_reduce_add_plane(const CUtensorMap* tmap, uint32_t smem_src, int x, int y, int z,
+                                                     int plane) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+        "r"(smem_src), "r"(x), "r"(y), "r"(z), "r"(plane)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_plane(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t mbar, int x, int y,
+                                               int z, int plane) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_dst),
+        "l"(tmap), "r"(mbar), "r"(x), "r"(y), "r"(z), "r"(plane)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have READ their shared-memory source (the CTA may exit / reuse it)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory (the warps' STS) become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// Bounded: a transfer that never completes (a bug) must not hang the GPU; returns false then.
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (int it = 0; it < (1 << 22); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+// first byte of the 128-byte aligned tile inside the dynamic shared memory (TMA needs 128-byte alignment)
+__device__ __forceinline__ float* align_tile(float* smem) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+    return smem + (((128u - (base & 127u)) & 127u) >> 2);
+}
+constexpr int kTmaParamWords = 8;  // s_tma: x0, y0, dx, dy, z0, plane (per CTA, read by the flushing lanes)
 
 #ifndef NFFT_REG_THREADS
 #define NFFT_REG_THREADS 256
@@ -280,7 +343,7 @@ __device__ __forceinline__ void for_each_quad3_rows(const Geom& g, const TileCtx
 inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
     // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
     return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * win_floats * 4 +
-           (size_t)(2 * nsc + 4) * 4 + (size_t)kRegMaxPts + 64;
+           (size_t)(2 * nsc + 4) * 4 + (size_t)kRegMaxPts + 64 + 128;  // + 128: tile aligned for TMA
 }
 
 // Loads the chunk's points, buckets them by supercell (column-major: z fastest) and leaves them in
@@ -390,38 +453,39 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
     __syncthreads();
 }
 
-// Work units of the 3D sweep: a column of supercells, or - when a column holds more than 1.5x the
-// average (clustered points) - up to 4 z-ranges of it with about equal point counts, so that one heavy
-// column does not leave the other warps of the CTA idle.  Unit = col | zb << 8 | ze << 16 (supercells
-// [zb, ze)); s_units[rank] is ordered longest first (LPT), *s_nunits counts the non-empty units (<= 64)
-// and must have been zeroed before the caller's last barrier.
+// Work units of the 3D sweep: the points of one column of supercells, or - when a column holds more than its
+// share of the chunk's points (clustered / dense data, where the fine sort keys make a chunk spatially compact)
+// - equal POINT ranges of it, so that one heavy column (or a single heavy supercell) is swept by several warps;
+// every unit adds its own partial register blocks into the tile.  Unit = col | lo << 8 | hi << 20 (positions
+// [lo, hi) of the bucketed point list, all inside the column); s_units[rank] is ordered longest first (LPT),
+// *s_nunits counts the units (<= 64) and must have been zeroed before the caller's last barrier.
 #ifndef NFFT_REG_SPLIT
 #define NFFT_REG_SPLIT 1
 #endif
-__device__ __forceinline__ void make_units(const int* s_start, int ncols, int nsz, int* s_units, int* s_nunits) {
+#ifndef NFFT_REG_UNITS
+#define NFFT_REG_UNITS (2 * kRegWarps)  // units a chunk is cut into when its columns are uneven
+#endif
+static_assert(kRegMaxPts < 4096, "unit encoding: 12 bits per point position");
+// s_expect (spread with the TMA flush, else nullptr): s_expect[p] = number of units that will add into plane
+// pair p of the tile -- a unit whose first / last point lies in supercell s0 / s1 of its column adds into the
+// pairs s0 * sp .. min(s1 * sp + zp, npairs) - 1, each exactly once (see advance() in the spread kernel).
+__device__ __forceinline__ void make_units(const int* s_start, int ncols, int nsz, int* s_units, int* s_nunits,
+                                           int* s_expect = nullptr, int sp = 0, int zp = 0, int npairs = 0) {
     __shared__ int s_raw[64], s_rawcnt[64];
     const int total = s_start[ncols * nsz] - s_start[0];
-    const int maxseg = NFFT_REG_SPLIT && ncols <= 32 ? (64 / ncols < 4 ? 64 / ncols : 4) : 1;  // ncols <= 64
+    const int maxseg = NFFT_REG_SPLIT && ncols <= 32 ? 16 : 1;  // sum of segments <= NFFT_REG_UNITS + ncols <= 64
     if ((int)threadIdx.x < ncols) {
         const int c0 = threadIdx.x * nsz;
         const int lo = s_start[c0], cnt = s_start[c0 + nsz] - lo;
-        int nseg = 1;
-        if (2 * cnt * ncols > 3 * total) nseg = (2 * cnt * ncols + 3 * total - 1) / (3 * total);  // ceil(cnt / 1.5 avg)
-        nseg = nseg < maxseg ? nseg : maxseg;
-        int zb = 0;
-        for (int j = 1; j <= nseg && cnt > 0; ++j) {
-            int ze = nsz;
-            if (j < nseg) {
-                const int target = lo + (int)((long long)cnt * j / nseg);
-                ze = zb;
-                while (ze < nsz && s_start[c0 + ze] < target) ++ze;  // first boundary at or above the target
-            }
-            const int ucnt = s_start[c0 + ze] - s_start[c0 + zb];
-            if (ucnt > 0) {
+        int nseg = (int)(((long long)cnt * NFFT_REG_UNITS + total / 2) / (total > 0 ? total : 1));  // round(cnt / share)
+        nseg = nseg < 1 ? 1 : (nseg > maxseg ? maxseg : nseg);
+        if (cnt < 2 * kRegGroup * nseg) nseg = cnt / (2 * kRegGroup) > 0 ? cnt / (2 * kRegGroup) : 1;  // >= 2 rounds each
+        for (int j = 0; j < nseg && cnt > 0; ++j) {
+            const int ulo = lo + (int)((long long)cnt * j / nseg), uhi = lo + (int)((long long)cnt * (j + 1) / nseg);
+            if (uhi > ulo) {
                 const int k = atomicAdd(s_nunits, 1);
-                s_raw[k] = (int)threadIdx.x | zb << 8 | ze << 16;
-                s_rawcnt[k] = ucnt;
-                zb = ze;
+                s_raw[k] = (int)threadIdx.x | ulo << 8 | uhi << 20;
+                s_rawcnt[k] = uhi - ulo;
             }
         }
     }
@@ -435,6 +499,16 @@ __device__ __forceinline__ void make_units(const int* s_start, int ncols, int ns
             rank += (oc > cnt || (oc == cnt && o < (int)threadIdx.x)) ? 1 : 0;
         }
         s_units[rank] = s_raw[threadIdx.x];
+        if (s_expect) {
+            const int unit = s_raw[threadIdx.x];
+            const int c0 = (unit & 0xff) * nsz, lo = (unit >> 8) & 0xfff, hi = (int)((unsigned)unit >> 20);
+            int s0 = 0;
+            while (s_start[c0 + s0 + 1] <= lo) ++s0;
+            int s1 = s0;
+            while (s_start[c0 + s1 + 1] < hi) ++s1;  // supercell of the unit's last point hi - 1
+            const int last = s1 * sp + zp < npairs ? s1 * sp + zp : npairs;
+            for (int p = s0 * sp; p < last; ++p) atomicAdd(&s_expect[p], 1);
+        }
     }
     __syncthreads();
 }
@@ -492,10 +566,10 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
 // ======================================================================================
 template <int LC, int SX, int SY, int SZ>
 __global__ void __launch_bounds__(kRegThreads, 2)
-spread_reg_kernel(const Geom g, const WindowArgs a) {
+spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
     constexpr int WX = Cfg::WX, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem_reg[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
     NFFT_PHASE_MARK(ph0);
@@ -503,7 +577,21 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
-    float* tile = smem;
+    float* tile = align_tile(smem_reg);
+    // TMA flush: plane pairs leave for the grid as soon as every unit that adds into them has done so
+    __shared__ int s_expect[32], s_done[32], s_tma[kTmaParamWords];
+    const int npairs = (g.P[2] + 1) / 2;
+    if (threadIdx.x < 32) s_expect[threadIdx.x] = 0, s_done[threadIdx.x] = 0;
+    if (a.use_tma && threadIdx.x == 0) {
+        // box origins of the tile; a tile that crosses the periodic boundary is added a second time, shifted by
+        // -+ M (out-of-range box elements are not written)
+        s_tma[0] = t.org[0];
+        s_tma[1] = t.org[1];
+        s_tma[2] = t.org[0] < 0 ? g.M : (t.org[0] + g.P[0] > g.M ? -g.M : 0);
+        s_tma[3] = t.org[1] < 0 ? g.M : (t.org[1] + g.P[1] > g.M ? -g.M : 0);
+        s_tma[4] = t.org[2];
+        s_tma[5] = t.b * g.C + a.k0;
+    }
     float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
     float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
     int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
@@ -513,7 +601,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     __shared__ int s_lock[64];  // one lock per pair of tile planes
     if (threadIdx.x < 64) s_lock[threadIdx.x] = 0;
 
-    for (int i = threadIdx.x; i < g.tile_elems; i += kRegThreads) tile[i] = 0.f;
+    for (int i = threadIdx.x; i < (g.tile_elems >> 2); i += kRegThreads)  // tile_elems is a multiple of 4
+        reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
     __shared__ int s_order[64], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
@@ -522,7 +611,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, a.use_tma ? s_expect : nullptr, SP, ZP, npairs);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(0, 5, ph0, pha);
     NFFT_PHASE_ADD(0, 6, pha, phb);
@@ -562,7 +651,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         if (col >= nunits) break;
         const int unit = s_order[col];
         col = unit & 0xff;
-        const int zb = (unit >> 8) & 0xff, ze = unit >> 16;
+        const int lo_seg = (unit >> 8) & 0xfff, hi_seg = (int)((unsigned)unit >> 20);  // never empty
         const int c0 = col * nsz;
         const int scx = col % nsx, scy = col / nsx;
         float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
@@ -622,7 +711,28 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
                     }
                     release_fence();
                     __syncwarp();
-                    if (lane == 0) atomicExch(lk, 0);
+                    if (lane == 0) {
+                        atomicExch(lk, 0);
+                        // the unit that completes a plane pair hands it to the TMA unit (no other warp will touch
+                        // it again); the sweep goes on while the reduction drains
+                        const int pr = scz * SP + kp;
+                        if (a.use_tma && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr]) {
+                            fence_acq_rel_cta();       // the other units' tile updates (ordered before their counts)
+                            fence_proxy_async_smem();  // ... become visible to the async proxy
+                            const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+                            const int x0 = s_tma[0], y0 = s_tma[1], dx = s_tma[2], dy = s_tma[3];
+                            for (int zz = 2 * pr; zz < 2 * pr + 2 && zz < g.P[2]; ++zz) {
+                                int gz = s_tma[4] + zz;
+                                gz = gz < 0 ? gz + g.M : (gz >= g.M ? gz - g.M : gz);
+                                const uint32_t src = tile_s + 4u * (uint32_t)(zz * g.sZ);
+                                tma_reduce_add_plane(&tmap, src, x0, y0, gz, s_tma[5]);
+                                if (dx) tma_reduce_add_plane(&tmap, src, x0 + dx, y0, gz, s_tma[5]);
+                                if (dy) tma_reduce_add_plane(&tmap, src, x0, y0 + dy, gz, s_tma[5]);
+                                if (dx && dy) tma_reduce_add_plane(&tmap, src, x0 + dx, y0 + dy, gz, s_tma[5]);
+                            }
+                            bulk_commit_group();
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -635,9 +745,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
         // Within the unit the points are staged in rounds of kRegGroup regardless of supercell
         // boundaries.
         {
-            const int lo_seg = s_start[c0 + zb], hi_seg = s_start[c0 + ze];  // never empty
-            int scz = zb, next_end = s_start[c0 + zb + 1];
-            while (next_end == lo_seg) {  // leading empty supercells: the block is still zero
+            int scz = 0, next_end = s_start[c0 + 1];
+            while (next_end <= lo_seg) {  // the unit's first point lies in supercell scz: the block is still zero
                 ++scz;
                 next_end = s_start[c0 + scz + 1];
             }
@@ -694,6 +803,12 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
     }
     NFFT_PHASE_WARP(0, ph1);
     NFFT_PHASE_MARK(ph2);
+    if (a.use_tma) {
+        // every plane pair has been handed to the TMA unit by the unit that completed it; the shared memory
+        // must stay allocated until the reductions this lane issued have read it
+        if (lane == 0) bulk_wait_read_all();
+        return;
+    }
     __syncthreads();
     NFFT_PHASE_MARK(ph3);
 
@@ -717,10 +832,10 @@ spread_reg_kernel(const Geom g, const WindowArgs a) {
 // ======================================================================================
 template <int LC, int SX, int SY, int SZ>
 __global__ void __launch_bounds__(kRegThreads, 2)
-gather_reg_kernel(const Geom g, const WindowArgs a) {
+gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
     constexpr int WX = Cfg::WX, WZ = Cfg::WZ, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem_reg[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
     NFFT_PHASE_MARK(ph0);
@@ -728,7 +843,11 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
-    float* tile = smem;
+    float* tile = align_tile(smem_reg);
+    __shared__ __align__(8) unsigned long long s_mbar;
+    // planes by TMA unless the tile crosses the periodic boundary in X or Y (a load zero-fills out-of-range
+    // elements, which would overwrite the wrapped half; the Z wrap is per plane)
+    const bool tma_tile = a.use_tma && t.org[0] >= 0 && t.org[0] + g.P[0] <= g.M && t.org[1] >= 0 && t.org[1] + g.P[1] <= g.M;
     float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
     float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
     int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
@@ -742,17 +861,34 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     // stage the padded tile (periodic wrap resolved per quad)
     // the tile travels with asynchronous copies while the points are loaded and bucketed (both phases
     // are latency-bound); complex grids: this pass's component of the interleaved pairs
-    {
+    if (tma_tile) {
+        if (threadIdx.x == 0) {
+            const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+            const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, (uint32_t)(g.P[2] * g.P[1] * g.P[0] * 4));
+            const int plane = t.b * g.C + a.k0;
+            for (int zz = 0; zz < g.P[2]; ++zz) {
+                int gz = t.org[2] + zz;
+                gz = gz < 0 ? gz + g.M : (gz >= g.M ? gz - g.M : gz);
+                tma_load_plane(tile_s + 4u * (uint32_t)(zz * g.sZ), &tmap, mbar, t.org[0], t.org[1], gz, plane);
+            }
+        }
+    } else {
         const int cs = g.cplx ? 2 : 1;
         const float* gsrc = a.grid + grid_plane(g, t.b, a.k0) + (g.cplx ? (a.k0 & 1) : 0);
         const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
         for_each_quad3_rows(g, t, [&](int so, long long cell) {
             const float* src = gsrc + cs * cell;
             const uint32_t dst = tile_s + 4u * (uint32_t)so;
-            cp_async4(dst, src);
-            cp_async4(dst + 4, src + cs);
-            cp_async4(dst + 8, src + 2 * cs);
-            cp_async4(dst + 12, src + 3 * cs);
+            if (cs == 1) {  // real grid: quads are 16-byte aligned on both sides (strides multiples of 4)
+                cp_async16(dst, src);
+            } else {
+                cp_async4(dst, src);
+                cp_async4(dst + 4, src + cs);
+                cp_async4(dst + 8, src + 2 * cs);
+                cp_async4(dst + 12, src + 3 * cs);
+            }
         });
     }
     __syncthreads();
@@ -760,7 +896,12 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-    cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
+    if (tma_tile) {
+        // every thread observes the completion itself (the mbarrier makes the TMA writes visible to its waiters)
+        if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0) && a.flags) atomicAdd(a.flags + 1, 1u);
+    } else {
+        cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
+    }
     make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(1, 5, ph0, pha);
@@ -797,13 +938,12 @@ gather_reg_kernel(const Geom g, const WindowArgs a) {
         if (col >= nunits) break;
         const int unit = s_order[col];
         col = unit & 0xff;
-        const int zb0 = (unit >> 8) & 0xff, ze0 = unit >> 16;
+        const int lo_col = (unit >> 8) & 0xfff, hi_col = (int)((unsigned)unit >> 20);  // never empty
         const int c0 = col * nsz;
         const int scx = col % nsx, scy = col / nsx;
         const float* cbase = tile + (scy * SY) * g.sY + scx * SX + padx;
-        const int lo_col = s_start[c0 + zb0], hi_col = s_start[c0 + ze0];  // never empty
-        int scz = zb0, next_end = s_start[c0 + zb0 + 1];
-        while (next_end == lo_col) {  // leading empty supercells
+        int scz = 0, next_end = s_start[c0 + 1];
+        while (next_end <= lo_col) {  // the unit's first point lies in supercell scz
             ++scz;
             next_end = s_start[c0 + scz + 1];
         }
