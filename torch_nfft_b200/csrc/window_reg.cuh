@@ -341,7 +341,7 @@ __device__ __forceinline__ void for_each_quad3_rows(const Geom& g, const TileCtx
 }
 
 inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
-    // tile | points (float4) | per-warp windows | supercell start[nsc+1], cursor[nsc] | offsets (u8)
+    // tile | points (float4) | offsets (u8) | per-warp windows | supercell start[nsc+2], cursor[nsc+2]
     return (size_t)g.tile_elems * 4 + (size_t)kRegMaxPts * 16 + (size_t)kRegWarps * win_floats * 4 +
            (size_t)(2 * nsc + 4) * 4 + (size_t)kRegMaxPts + 64 + 128;  // + 128: tile aligned for TMA
 }
@@ -466,6 +466,7 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
 #define NFFT_REG_UNITS (2 * kRegWarps)  // units a chunk is cut into when its columns are uneven
 #endif
 static_assert(kRegMaxPts < 4096, "unit encoding: 12 bits per point position");
+static_assert(kRegMaxPts % 16 == 0, "the tap windows behind the u8 offsets must stay 16-byte aligned");
 // s_expect (spread with the TMA flush, else nullptr): s_expect[p] = number of units that will add into plane
 // pair p of the tile -- a unit whose first / last point lies in supercell s0 / s1 of its column adds into the
 // pairs s0 * sp .. min(s1 * sp + zp, npairs) - 1, each exactly once (see advance() in the spread kernel).
@@ -515,29 +516,42 @@ __device__ __forceinline__ void make_units(const int* s_start, int ncols, int ns
 
 // Phase A of a warp round: the taps of up to kRegGroup points are evaluated and stored at their
 // shifted positions inside zero-initialised windows.  Lane <-> (point, dimension): each lane runs
-// L independent expf chains (unrolled), so the latency of one tap hides behind the others.
+// L independent exp chains (unrolled), so the latency of one tap hides behind the others.
 // SCALE_Z: the z taps carry the point's value (spread), so the sweep multiplies only psi(Y) * psi(X).
+// All shared-memory traffic goes through two opaque shared-window addresses -- `wbase` (this warp's windows)
+// and `pts_sh` (the CTA's point records, with the u8 cell offsets kRegMaxPts * 16 bytes behind them): at 128
+// registers ptxas otherwise rebuilds the three array bases from the kernel parameters in every round
+// (S2R / S2UR / LDC / ULEA / UIMAD chains: 45 of the ~100 instructions a round spent before its first tap).
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "f"(0.f) : "memory");
+}
 template <typename Cfg, int LC, bool SCALE_Z = false>
-__device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
-                                              int npts, float* win, int lane, bool pow2) {
+__device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, int base, int npts, uint32_t wbase, int lane,
+                                              bool pow2) {
     constexpr int kQuads = Cfg::WIN_FLOATS / 4;
 #pragma unroll
     for (int k = 0; k < (kQuads + 31) / 32; ++k) {
         const int qd = lane + 32 * k;
-        if (qd < kQuads) reinterpret_cast<float4*>(win)[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qd < kQuads) sts_zero16(wbase + 16u * (uint32_t)qd);
     }
     __syncwarp();
     const int pt = lane / 3, api = lane - pt * 3;  // API dim 0,1,2 <-> slot Z,Y,X
     if (pt < npts) {
         const int slot = 2 - api;
-        const float p = reinterpret_cast<const float*>(s_pts + base + pt)[api];
-        const int off = (s_off[base + pt] >> (2 * slot)) & 3;
+        const uint32_t rec = pts_sh + 16u * (uint32_t)(base + pt);
+        const float p = lds_at(rec + 4u * (uint32_t)api);
+        const int off = (int)(lds_u8(pts_sh + (uint32_t)(kRegMaxPts * 16 + base + pt)) >> (2 * slot)) & 3;
         constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;
-        float* dst = slot == 2 ? win + kXY + pt * Cfg::ZWP + off : win + (2 * pt + slot) * Cfg::XYP + off;
+        const uint32_t dst = wbase + 4u * (uint32_t)((slot == 2 ? kXY + pt * Cfg::ZWP : (2 * pt + slot) * Cfg::XYP) + off);
         const float pm = p * (float)g.M;
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
         float amp = g.inv_sqrt_b_pi;
-        if (SCALE_Z && slot == 2) amp *= s_pts[base + pt].w;
+        if (SCALE_Z && slot == 2) amp *= lds_at(rec + 12u);
         if (pow2) {
             // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
             // rounded, i.e. identical to the reference's double evaluation (:84-86)
@@ -547,14 +561,14 @@ __device__ __forceinline__ void stage_windows(const Geom& g, const float4* s_pts
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
-                dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;  // eval_phi, :24-28
+                sts_at(dst + 4u * l, window_exp(-(tt * tt) * g.inv_b) * amp);  // eval_phi, :24-28
             }
         } else {
             const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = (float)(bd - (double)l);
-                dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;
+                sts_at(dst + 4u * l, window_exp(-(tt * tt) * g.inv_b) * amp);
             }
         }
     }
@@ -592,11 +606,13 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
         s_tma[4] = t.org[2];
         s_tma[5] = t.b * g.C + a.k0;
     }
+    // tile | points (float4) | cell offsets (u8, right behind the points: one base address serves both in the
+    // tap staging) | per-warp tap windows | supercell start[nsc + 2], cursor[nsc + 2]
     float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
-    float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
+    unsigned char* s_off = reinterpret_cast<unsigned char*>(s_pts + kRegMaxPts);
+    float* s_win = reinterpret_cast<float*>(s_off + kRegMaxPts);
     int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
     int* s_cur = s_start + nsc + 2;
-    unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
     __shared__ int s_next;
     __shared__ int s_lock[64];  // one lock per pair of tile planes
     if (threadIdx.x < 64) s_lock[threadIdx.x] = 0;
@@ -635,6 +651,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     }
     uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
     asm volatile("" : "+r"(wbase));
+    uint32_t pts_sh = (uint32_t)__cvta_generic_to_shared(s_pts);
+    asm volatile("" : "+r"(pts_sh));
     uint32_t awi[CPL], awj[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
@@ -752,7 +770,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
             }
             for (int base = lo_seg; base < hi_seg; base += kRegGroup) {
                 const int npts = hi_seg - base < kRegGroup ? hi_seg - base : kRegGroup;
-                stage_windows<Cfg, LC, true>(g, s_pts, s_off, base, npts, win, lane, pow2);
+                stage_windows<Cfg, LC, true>(g, pts_sh, base, npts, wbase, lane, pow2);
                 // One copy of the point body per slot of the round (window loads with immediate offsets),
                 // entered through a switch; a slot that ends a supercell leaves the switch so that the ONE
                 // copy of the add-out code above it runs, and the switch is re-entered at the next slot.
@@ -848,11 +866,13 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     // planes by TMA unless the tile crosses the periodic boundary in X or Y (a load zero-fills out-of-range
     // elements, which would overwrite the wrapped half; the Z wrap is per plane)
     const bool tma_tile = a.use_tma && t.org[0] >= 0 && t.org[0] + g.P[0] <= g.M && t.org[1] >= 0 && t.org[1] + g.P[1] <= g.M;
+    // tile | points (float4) | cell offsets (u8, right behind the points: one base address serves both in the
+    // tap staging) | per-warp tap windows | supercell start[nsc + 2], cursor[nsc + 2]
     float4* s_pts = reinterpret_cast<float4*>(tile + g.tile_elems);
-    float* s_win = reinterpret_cast<float*>(s_pts + kRegMaxPts);
+    unsigned char* s_off = reinterpret_cast<unsigned char*>(s_pts + kRegMaxPts);
+    float* s_win = reinterpret_cast<float*>(s_off + kRegMaxPts);
     int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
     int* s_cur = s_start + nsc + 2;
-    unsigned char* s_off = reinterpret_cast<unsigned char*>(s_cur + nsc + 2);
     __shared__ int s_next;
 
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
@@ -924,6 +944,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     }
     uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
     asm volatile("" : "+r"(wbase));
+    uint32_t pts_sh = (uint32_t)__cvta_generic_to_shared(s_pts);
+    asm volatile("" : "+r"(pts_sh));
     uint32_t awi[CPL], awj[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
@@ -982,7 +1004,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
 
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
-            stage_windows<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            stage_windows<Cfg, LC>(g, pts_sh, base, npts, wbase, lane, pow2);
             // As in the spread: one copy of the point body per slot (window loads with immediate offsets, the
             // partial sum in a static register), entered through a switch; a slot that ends a supercell
             // leaves the switch so that the ONE copy of the block slide runs.  (An unrolled loop carries a
