@@ -414,6 +414,36 @@ fill_items_kernel(const uint32_t* __restrict__ bin_start, const uint32_t* __rest
     }
 }
 
+// Small problems (one radix pass whose digit IS the bin: <= 256 bins, no fine key bits -- e.g. the 1D workload
+// c2): bin offsets come straight from the scanned digit table (entry [digit][block 0] = number of keys with a
+// smaller digit), so one block derives bin_start, the chunk counts, their scan and the work items: one launch
+// instead of five (count_sorted, scan, chunk_count, scan, fill_items) on a launch-bound path.
+__global__ void __launch_bounds__(kRsBins)
+finish_single_pass_kernel(const uint32_t* __restrict__ table_scanned, int nblocks, int nbins, uint32_t n, int pmax,
+                          uint32_t* __restrict__ bin_start, uint32_t* __restrict__ chunk_start,
+                          uint4* __restrict__ items) {
+    __shared__ uint32_t s_warp[33];
+    const int b = threadIdx.x;
+    uint32_t lo = 0, hi = 0;
+    if (b < nbins) {
+        lo = table_scanned[(long long)b * nblocks];
+        hi = b + 1 < kRsBins ? table_scanned[(long long)(b + 1) * nblocks] : n;
+        bin_start[b] = lo;
+        if (b == nbins - 1) bin_start[nbins] = n;
+    }
+    const uint32_t cnt = hi - lo;
+    const uint32_t nch = b < nbins ? (cnt + (uint32_t)pmax - 1u) / (uint32_t)pmax : 0u;
+    uint32_t total;
+    const uint32_t first = block_excl_scan(nch, s_warp, &total);
+    if (b < nbins) {
+        chunk_start[b] = first;
+        if (b == nbins - 1) chunk_start[nbins] = total;
+        for (uint32_t c = 0; c < nch; ++c)
+            items[first + c] = make_uint4((uint32_t)b, lo + (uint32_t)((unsigned long long)cnt * c / nch),
+                                          lo + (uint32_t)((unsigned long long)cnt * (c + 1) / nch), 0u);
+    }
+}
+
 // ------------------------------------------------------------------------- host orchestration
 // The binning result that the window kernels read ("point plan", persistent) and the scratch the sort
 // needs while it runs (transient) are separate regions, so that a caller can keep the plan of a point
@@ -543,6 +573,13 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
                       table, (int)L.nblocks);
             kin = kout;
             iin = iout;
+        }
+        if (passes == 1 && g.fine_bits == 0 && nbins <= kRsBins) {
+            // the digit is the bin: everything after the scatter in one small launch
+            NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)plan->max_items * sizeof(uint4), st));
+            NF_LAUNCH(finish_single_pass_kernel, 1, kRsBins, 0, st, table, (int)L.nblocks, (int)nbins, (uint32_t)n,
+                      g.pmax, bin_start, chunk_start, plan->items);
+            return NFFTB200_OK;
         }
         if (passes > 0) {
             NF_LAUNCH(count_sorted_kernel, (unsigned)((n + 255) / 256), 256, 0, st, kin, n, g.fine_bits, bin_count);

@@ -196,7 +196,7 @@ __device__ __forceinline__ float window_exp(float x) {
 #define NFFT_REG_LOCK_TTAS 0
 #endif
 #ifndef NFFT_REG_LOCK_NS
-#define NFFT_REG_LOCK_NS 32
+#define NFFT_REG_LOCK_NS 0
 #endif
 #ifndef NFFT_REG_LOCK_EXCH
 #define NFFT_REG_LOCK_EXCH 0
