@@ -118,7 +118,10 @@ static void choose_strides(Geom& g) {
     g.sY = g.P[0];
     g.sZ = g.P[0] * g.P[1];
     if (g.dim == 1) return;
-    if (g.use_reg == 1) {
+#ifndef NFFT_REG_OLD_STRIDES
+#define NFFT_REG_OLD_STRIDES 0  // bisect aid: the searched strides (no TMA then: planes are not 128-byte aligned)
+#endif
+    if (g.use_reg == 1 && !NFFT_REG_OLD_STRIDES) {
         // 3D register-stencil kernels: rows dense (a TMA box plane is P0 x P1 floats, row pitch P0), planes
         // 128-byte aligned (TMA shared-memory address).  Bank conflicts of the sweep's (x, y)-position accesses
         // are the same for sY = 28 as for the previous 29 (1.83 wavefronts per access at L = 10).

@@ -81,6 +81,26 @@ __device__ __forceinline__ float* align_tile(float* smem) {
 }
 constexpr int kTmaParamWords = 8;  // s_tma: x0, y0, dx, dy, z0, plane (per CTA, read by the flushing lanes)
 
+// Hands one finished plane pair of the spread tile to the TMA unit (executed by ONE lane).  Out of line on
+// purpose: the sweep has seven add-out sites, and the inlined copies (110 instructions each) pushed the kernel
+// from 65 KB to 98 KB of code -- instruction-cache misses in the hot loop cost more than the flush saved.
+__device__ __noinline__ void tma_flush_plane_pair(const CUtensorMap* tmap, uint32_t tile_s, const int* s_tma, int pr,
+                                                  int nplanes, int plane_floats, int M) {
+    fence_acq_rel_cta();       // the other units' tile updates (ordered before their completion counts)
+    fence_proxy_async_smem();  // ... become visible to the async proxy
+    const int x0 = s_tma[0], y0 = s_tma[1], dx = s_tma[2], dy = s_tma[3], plane = s_tma[5];
+    for (int zz = 2 * pr; zz < 2 * pr + 2 && zz < nplanes; ++zz) {
+        int gz = s_tma[4] + zz;
+        gz = gz < 0 ? gz + M : (gz >= M ? gz - M : gz);
+        const uint32_t src = tile_s + 4u * (uint32_t)(zz * plane_floats);
+        tma_reduce_add_plane(tmap, src, x0, y0, gz, plane);
+        if (dx) tma_reduce_add_plane(tmap, src, x0 + dx, y0, gz, plane);
+        if (dy) tma_reduce_add_plane(tmap, src, x0, y0 + dy, gz, plane);
+        if (dx && dy) tma_reduce_add_plane(tmap, src, x0 + dx, y0 + dy, gz, plane);
+    }
+    bulk_commit_group();
+}
+
 #ifndef NFFT_REG_THREADS
 #define NFFT_REG_THREADS 256
 #endif
@@ -575,6 +595,54 @@ __device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, in
     __syncwarp();
 }
 
+// bisect aid (-DNFFT_REG_OLD_STAGE=1): the previous tap staging through generic pointers
+#ifndef NFFT_REG_OLD_STAGE
+#define NFFT_REG_OLD_STAGE 0
+#endif
+template <typename Cfg, int LC, bool SCALE_Z = false>
+__device__ __forceinline__ void stage_windows_generic(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
+                                              int npts, float* win, int lane, bool pow2) {
+    constexpr int kQuads = Cfg::WIN_FLOATS / 4;
+#pragma unroll
+    for (int k = 0; k < (kQuads + 31) / 32; ++k) {
+        const int qd = lane + 32 * k;
+        if (qd < kQuads) reinterpret_cast<float4*>(win)[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    const int pt = lane / 3, api = lane - pt * 3;  // API dim 0,1,2 <-> slot Z,Y,X
+    if (pt < npts) {
+        const int slot = 2 - api;
+        const float p = reinterpret_cast<const float*>(s_pts + base + pt)[api];
+        const int off = (s_off[base + pt] >> (2 * slot)) & 3;
+        constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;
+        float* dst = slot == 2 ? win + kXY + pt * Cfg::ZWP + off : win + (2 * pt + slot) * Cfg::XYP + off;
+        const float pm = p * (float)g.M;
+        const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
+        float amp = g.inv_sqrt_b_pi;
+        if (SCALE_Z && slot == 2) amp *= s_pts[base + pt].w;
+        if (pow2) {
+            // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
+            // rounded, i.e. identical to the reference's double evaluation (:84-86)
+            // frac = pm - fl is exact; frac + (m - l) is ONE rounding of the exact value, i.e. bit-identical
+            // to the reference's (float)((double)pos * 2N - shift - l)
+            const float frac = pm - fl;
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
+                dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;  // eval_phi, :24-28
+            }
+        } else {
+            const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                const float tt = (float)(bd - (double)l);
+                dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // ======================================================================================
 // spread
 // ======================================================================================
@@ -734,22 +802,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                         // the unit that completes a plane pair hands it to the TMA unit (no other warp will touch
                         // it again); the sweep goes on while the reduction drains
                         const int pr = scz * SP + kp;
-                        if (a.use_tma && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr]) {
-                            fence_acq_rel_cta();       // the other units' tile updates (ordered before their counts)
-                            fence_proxy_async_smem();  // ... become visible to the async proxy
-                            const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-                            const int x0 = s_tma[0], y0 = s_tma[1], dx = s_tma[2], dy = s_tma[3];
-                            for (int zz = 2 * pr; zz < 2 * pr + 2 && zz < g.P[2]; ++zz) {
-                                int gz = s_tma[4] + zz;
-                                gz = gz < 0 ? gz + g.M : (gz >= g.M ? gz - g.M : gz);
-                                const uint32_t src = tile_s + 4u * (uint32_t)(zz * g.sZ);
-                                tma_reduce_add_plane(&tmap, src, x0, y0, gz, s_tma[5]);
-                                if (dx) tma_reduce_add_plane(&tmap, src, x0 + dx, y0, gz, s_tma[5]);
-                                if (dy) tma_reduce_add_plane(&tmap, src, x0, y0 + dy, gz, s_tma[5]);
-                                if (dx && dy) tma_reduce_add_plane(&tmap, src, x0 + dx, y0 + dy, gz, s_tma[5]);
-                            }
-                            bulk_commit_group();
-                        }
+                        if (a.use_tma && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr])
+                            tma_flush_plane_pair(&tmap, (uint32_t)__cvta_generic_to_shared(tile), s_tma, pr, g.P[2], g.sZ,
+                                                 g.M);
                     }
                 }
             }
@@ -770,7 +825,11 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
             }
             for (int base = lo_seg; base < hi_seg; base += kRegGroup) {
                 const int npts = hi_seg - base < kRegGroup ? hi_seg - base : kRegGroup;
+#if NFFT_REG_OLD_STAGE
+                stage_windows_generic<Cfg, LC, true>(g, s_pts, s_off, base, npts, win, lane, pow2);
+#else
                 stage_windows<Cfg, LC, true>(g, pts_sh, base, npts, wbase, lane, pow2);
+#endif
                 // One copy of the point body per slot of the round (window loads with immediate offsets),
                 // entered through a switch; a slot that ends a supercell leaves the switch so that the ONE
                 // copy of the add-out code above it runs, and the switch is re-entered at the next slot.
@@ -1004,7 +1063,11 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
 
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
+#if NFFT_REG_OLD_STAGE
+            stage_windows_generic<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
+#else
             stage_windows<Cfg, LC>(g, pts_sh, base, npts, wbase, lane, pow2);
+#endif
             // As in the spread: one copy of the point body per slot (window loads with immediate offsets, the
             // partial sum in a static register), entered through a switch; a slot that ends a supercell
             // leaves the switch so that the ONE copy of the block slide runs.  (An unrolled loop carries a
