@@ -170,8 +170,9 @@ int nfftb200_sort_points(const float* pos, const int64_t* batch, uint32_t* keys_
                          int m, int64_t B, int64_t C, int flags, void* workspace,
                          size_t workspace_bytes, void* stream);
 
-/* Host-only: the tiling the engine would use.  out[22] = dim,N,M,m,L, T[3], nt[3], P[3], sY, sZ,
- * tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits (slot order X,Y,Z). */
+/* Host-only: the tiling the engine would use.  out[25] = dim,N,M,m,L, T[3], nt[3], P[3], sY, sZ,
+ * tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits, supercell[3] (slot order X,Y,Z; see
+ * DESIGN.md). */
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n,
                             int32_t* out);
 

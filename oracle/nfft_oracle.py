@@ -420,9 +420,9 @@ def tile_keys(pos, batch, N, tile):
 
 
 def sort_keys(pos, batch, N, tile, fine_bits=0, supercell=(2, 4, 4)):
-    """The engine's full sort key: tile key << fine_bits | top fine_bits bits of the 7-bit hierarchical index
-    [y half | x half | y quarter | x quarter | z supercell] of the point's supercell inside its 16^3 tile
-    (the engine's own binning rule, torch_nfft_b200/csrc/sort.cuh: fine_index; 3D only).
+    """The engine's full sort key: tile key << fine_bits | top fine_bits bits of the hierarchical index of the
+    point's supercell inside its 16^3 tile -- per level from halves down to single supercells a (y bit, x bit)
+    pair, then the z supercell (the engine's own binning rule, torch_nfft_b200/csrc/sort.cuh: fine_index; 3D only).
     `tile` / `supercell` are in API dimension order (dim 0 = slot Z ... dim 2 = slot X)."""
     key = tile_keys(pos, batch, N, tile)
     if fine_bits == 0:
@@ -433,8 +433,13 @@ def sort_keys(pos, batch, N, tile, fine_bits=0, supercell=(2, 4, 4)):
     cw = np.mod(compute_cells(pos32, M), M)
     inside = cw - (cw // np.asarray(tile)) * np.asarray(tile)
     bz, by, bx = (inside[:, a] // supercell[a] for a in range(3))
-    fine = ((by >> 1) << 6) | ((bx >> 1) << 5) | ((by & 1) << 4) | ((bx & 1) << 3) | bz
-    return ((key << fine_bits) | (fine >> (7 - fine_bits))).astype(np.int64)
+    levels = int(np.log2(tile[2] // supercell[2]))       # supercells per tile edge in x (= y): 2^levels
+    zbits = int(np.log2(tile[0] // supercell[0]))
+    fine = np.zeros_like(key)
+    for b in range(levels - 1, -1, -1):
+        fine = (fine << 2) | (((by >> b) & 1) << 1) | ((bx >> b) & 1)
+    fine = (fine << zbits) | bz
+    return ((key << fine_bits) | (fine >> (2 * levels + zbits - fine_bits))).astype(np.int64)
 
 
 def stable_permutation(keys):

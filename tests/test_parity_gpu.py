@@ -156,8 +156,8 @@ def test_binning_is_bit_exact(d, N, m, B, n):
                                           ctypes.cast(tile, ctypes.c_void_p), nn, d, N, m, B, 1, 0, ws.data_ptr(),
                                           ws.numel(), torch.cuda.current_stream().cuda_stream), "sort")
         torch.cuda.synchronize()
-        fine = _lib.geometry(d, N, m, B, 1, 0, nn)["fine_bits"]
-        okeys = O.sort_keys(pos, batch, N, list(tile)[:d][::-1], fine)
+        geo = _lib.geometry(d, N, m, B, 1, 0, nn)
+        okeys = O.sort_keys(pos, batch, N, list(tile)[:d][::-1], geo["fine_bits"], (geo["scz"], geo["scy"], geo["scx"]))
         assert np.array_equal(keys.cpu().numpy().astype(np.int64), okeys)
         assert np.array_equal(perm.cpu().numpy().astype(np.int64), O.stable_permutation(okeys))
 
@@ -415,7 +415,7 @@ def test_stale_plan_is_detected_and_never_writes_out_of_bounds():
     `.data`, another CUDA graph, a custom kernel: nothing the engine can see), the transforms drop the points
     they find outside their tile and count them instead of indexing shared memory out of bounds."""
     rng = np.random.default_rng(12)
-    for d, N, m in [(3, 32, 4), (2, 32, 4), (1, 1024, 8), (3, 32, 6), (2, 32, 2)]:  # reg 3D / reg 2D / 1D (4 tiles) / team 3D / team 2D
+    for d, N, m in [(3, 32, 4), (2, 32, 4), (1, 1024, 8), (3, 32, 6), (2, 128, 2)]:  # reg 3D / reg 2D / 1D / team 3D / team 2D, several tiles each
         pos, batch = make_points(rng, d, 2, 3000)
         x = make_values(rng, (pos.shape[0], 1), False)
         tp, tb, tx = cuda(pos), cuda(batch), cuda(x)

@@ -98,12 +98,12 @@ def launch_count() -> int:
 
 
 GEOMETRY_FIELDS = ("dim", "N", "M", "m", "L", "Tx", "Ty", "Tz", "ntx", "nty", "ntz", "Px", "Py", "Pz", "sY", "sZ",
-                   "tile_elems", "ncomp", "pmax", "spread_threads", "use_reg", "fine_bits")
+                   "tile_elems", "ncomp", "pmax", "spread_threads", "use_reg", "fine_bits", "scx", "scy", "scz")
 
 
 def geometry(d, N, m, B=1, C=1, flags=0, n=0):
     """Tiling the engine uses for a transform (host-only query)."""
-    out = (ctypes.c_int32 * 22)()
+    out = (ctypes.c_int32 * 25)()
     check(lib().nfftb200_debug_geometry(d, N, m, B, C, flags, n, ctypes.cast(out, ctypes.c_void_p)), "geometry")
     return dict(zip(GEOMETRY_FIELDS, list(out)))
 

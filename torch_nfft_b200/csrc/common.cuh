@@ -85,7 +85,8 @@ struct Geom {
     int spread_threads;  // block size of the spread kernel
     int use_reg;         // 1: register-stencil kernels (window_reg.cuh), 0: team kernels (window.cuh)
     int fine_bits;       // low bits of a sort key: position of the point's supercell inside its tile (sort.cuh)
-    int sc[3];           // supercell extent per slot the fine bits refer to
+    int sc[3];           // supercell extent per slot (3D register-stencil kernels: 4 x 4 x 2, dense point sets 2 x 2 x 2)
+    int fine_xy_levels, fine_z_bits;  // log2 of the supercells per tile edge in X / Y, and in Z
     float inv_b, inv_sqrt_b_pi, c_hat;
 };
 

@@ -242,24 +242,37 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     g.tiles_per_batch = g.nt[0] * g.nt[1] * g.nt[2];
     if ((long long)g.tiles_per_batch * B >= (1ll << 31)) NF_FAIL(NFFTB200_ERR_INVALID, "too many tiles");
 
-    // Fine sort-key bits (sort.cuh: fine_index): only for the 3D register-stencil tiling with full 16^3 tiles of
-    // 4 x 4 x 2 supercells.  The bits that fit the radix passes the tile key needs anyway are free; a dense point
-    // set (>= 1 point per oversampled cell on average: c5) gets all of them even if that adds a pass, because
-    // its tiles are cut into many chunks and the sweep gains far more than the pass costs.
-    g.fine_bits = 0;
+    // Supercells and fine sort-key bits of the 3D register-stencil kernels (full 16^3 tiles only).
+    // * A dense point set (>= 1 point per oversampled cell on average, known on the host: BASELINE c5) is swept
+    //   with 2 x 2 x 2 supercells: the register block shrinks from 13 x 13 to 11 x 11 positions (4 instead of 6
+    //   per lane, 24 instead of 36 FFMA2 per point); its add-outs, 4x as frequent per cell, are amortised over
+    //   the many points of a supercell.  Everything else uses 4 x 4 x 2.
+    // * Fine key bits (sort.cuh: fine_index): the bits that fit the radix passes the tile key needs anyway are
+    //   free; a dense set gets all of them even if that adds a pass, because its tiles are cut into many chunks
+    //   and compact chunks are what lets the points of a chunk share register blocks.
+    g.fine_bits = g.fine_xy_levels = g.fine_z_bits = 0;
     g.sc[0] = g.sc[1] = g.sc[2] = 1;
     static const bool no_fine = getenv("NFFTB200_NO_FINE_SORT") != nullptr;
-    if (g.use_reg == 1 && !no_fine && kRegSX == 4 && kRegSY == 4 && kRegSZ == 2 && g.T[0] == 16 && g.T[1] == 16 &&
-        g.T[2] == 16) {
-        g.sc[0] = kRegSX, g.sc[1] = kRegSY, g.sc[2] = kRegSZ;
-        int tile_bits = 0;
-        while ((1ll << tile_bits) < (long long)g.tiles_per_batch * B) ++tile_bits;
-        const int spare = (tile_bits + 7) / 8 * 8 - tile_bits;
+    static const bool no_dense = getenv("NFFTB200_NO_DENSE") != nullptr;
+    if (g.use_reg == 1) {
+        const bool full_tiles = g.T[0] == 16 && g.T[1] == 16 && g.T[2] == 16;
         const bool dense = (double)n_points >= (double)B * (double)g.Md;
-        int k = dense ? kFineBitsMax : (spare < kFineBitsMax ? spare : kFineBitsMax);
-        if (tile_bits == 0 && !dense) k = 0;  // a single tile and few points: no radix pass at all
-        if (k > 31 - tile_bits) k = 31 - tile_bits;
-        g.fine_bits = k < 0 ? 0 : k;
+        g.sc[0] = kRegSX, g.sc[1] = kRegSY, g.sc[2] = kRegSZ;
+        if (dense && full_tiles && !no_dense && (m == 3 || m == 4)) g.sc[0] = g.sc[1] = g.sc[2] = 2;
+        auto log2i = [](int v) { int b = 0; while ((1 << b) < v) ++b; return b; };
+        const bool pow2_cells = g.sc[0] == g.sc[1] && (g.sc[0] & (g.sc[0] - 1)) == 0 && (g.sc[2] & (g.sc[2] - 1)) == 0;
+        if (full_tiles && pow2_cells && !no_fine) {
+            g.fine_xy_levels = log2i(16 / g.sc[0]);
+            g.fine_z_bits = log2i(16 / g.sc[2]);
+            const int total = 2 * g.fine_xy_levels + g.fine_z_bits;
+            int tile_bits = 0;
+            while ((1ll << tile_bits) < (long long)g.tiles_per_batch * B) ++tile_bits;
+            const int spare = (tile_bits + 7) / 8 * 8 - tile_bits;
+            int k = dense ? total : (spare < total ? spare : total);
+            if (tile_bits == 0 && !dense) k = 0;  // a single tile and few points: no radix pass at all
+            if (k > 31 - tile_bits) k = 31 - tile_bits;
+            g.fine_bits = k < 0 ? 0 : k;
+        }
     }
 
     const int team = d == 1 ? g.L : g.L * g.L;
@@ -447,6 +460,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         // 6 positions x 6 float2 accumulators per lane
         WindowKernelTma kern = nullptr;
         int win_floats = 0;
+        const bool small_cells = g.sc[0] == 2 && g.sc[1] == 2 && g.sc[2] == 2;  // dense point sets, m = 3, 4
         switch (g.m) {
 #define NF_REG_CASE(M_, L_)                                                                          \
             case M_:                                                                                 \
@@ -454,14 +468,26 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
                               : gather_reg_kernel<L_, kRegSX, kRegSY, kRegSZ>;                       \
                 win_floats = RegCfg<L_, kRegSX, kRegSY, kRegSZ>::WIN_FLOATS;                         \
                 break;
+#define NF_REG_CASE_DENSE(M_, L_)                                                                    \
+            case M_:                                                                                 \
+                if (small_cells) {                                                                   \
+                    kern = spread ? spread_reg_kernel<L_, 2, 2, 2> : gather_reg_kernel<L_, 2, 2, 2>; \
+                    win_floats = RegCfg<L_, 2, 2, 2>::WIN_FLOATS;                                    \
+                } else {                                                                             \
+                    kern = spread ? spread_reg_kernel<L_, kRegSX, kRegSY, kRegSZ>                    \
+                                  : gather_reg_kernel<L_, kRegSX, kRegSY, kRegSZ>;                   \
+                    win_floats = RegCfg<L_, kRegSX, kRegSY, kRegSZ>::WIN_FLOATS;                     \
+                }                                                                                    \
+                break;
             NF_REG_CASE(1, 4)
             NF_REG_CASE(2, 6)
-            NF_REG_CASE(3, 8)
-            NF_REG_CASE(4, 10)
+            NF_REG_CASE_DENSE(3, 8)
+            NF_REG_CASE_DENSE(4, 10)
 #undef NF_REG_CASE
+#undef NF_REG_CASE_DENSE
             default: NF_FAIL(NFFTB200_ERR_INVALID, "register-stencil kernels need m <= 4");
         }
-        const int nsc = ((g.T[0] + kRegSX - 1) / kRegSX) * ((g.T[1] + kRegSY - 1) / kRegSY) * ((g.T[2] + kRegSZ - 1) / kRegSZ);
+        const int nsc = ((g.T[0] + g.sc[0] - 1) / g.sc[0]) * ((g.T[1] + g.sc[1] - 1) / g.sc[1]) * ((g.T[2] + g.sc[2] - 1) / g.sc[2]);
         const size_t smem = reg_smem_bytes(g, nsc, win_floats);
         NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
         CUtensorMap tmap;
@@ -826,13 +852,14 @@ int nfftb200_version(void) { return 200; }
 const char* nfftb200_last_error(void) { return g_err; }
 int64_t nfftb200_launch_count(void) { return (int64_t)g_launches.load(); }
 
-// out[0..21] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits
+// out[0..24] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits, sc[3]
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n, int32_t* out) {
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    int v[22] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
-                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg, g.fine_bits};
-    for (int i = 0; i < 22; ++i) out[i] = v[i];
+    int v[25] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
+                 g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg, g.fine_bits, g.sc[0], g.sc[1],
+                 g.sc[2]};
+    for (int i = 0; i < 25; ++i) out[i] = v[i];
     return NFFTB200_OK;
 }
 

@@ -186,16 +186,18 @@ __device__ __forceinline__ long long batch_of(const BatchRef& br, long long i) {
     return lo;
 }
 
-// Fine part of a key (3D register-stencil tiling, 16^3 tiles of 4 x 4 x 2 supercells): the supercell of the
-// point inside its tile as a HIERARCHICAL index, most significant first
-//   [ y half | x half | y quarter | x quarter | z supercell (3 bits) ]
-// of which the top g.fine_bits bits are kept.  Sorting by (tile, fine) makes the chunks a heavy tile is cut
-// into spatially compact -- a quadrant, a supercell column, a z-range of it -- instead of random samples of
-// the whole tile, so the points of a chunk share register blocks in the sweep (window_reg.cuh).
-constexpr int kFineBitsMax = 7;
+// Fine part of a key (3D register-stencil tiling: 16^3 tiles of sc[0] x sc[1] x sc[2] supercells, all counts powers
+// of two): the supercell of the point inside its tile as a HIERARCHICAL index, most significant first
+//   [ y bit, x bit ] per level from halves down to single supercells, then the z supercell
+// (4 x 4 x 2 supercells: 7 bits, 2 x 2 x 2: 9 bits) of which the top g.fine_bits bits are kept.  Sorting by
+// (tile, fine) makes the chunks a heavy tile is cut into spatially compact -- a quadrant, a supercell column,
+// a z-range of it -- instead of random samples of the whole tile, so the points of a chunk share register
+// blocks in the sweep (window_reg.cuh).
 __device__ __forceinline__ uint32_t fine_index(int cx, int cy, int cz, const Geom& g) {
-    const int bx = cx / g.sc[0], by = cy / g.sc[1], bz = cz / g.sc[2];  // < 4, < 4, < 8
-    return (uint32_t)(((by >> 1) << 6) | ((bx >> 1) << 5) | ((by & 1) << 4) | ((bx & 1) << 3) | bz);
+    const int bx = cx / g.sc[0], by = cy / g.sc[1], bz = cz / g.sc[2];
+    uint32_t f = 0;
+    for (int b = g.fine_xy_levels - 1; b >= 0; --b) f = (f << 2) | (uint32_t)((((by >> b) & 1) << 1) | ((bx >> b) & 1));
+    return (f << g.fine_z_bits) | (uint32_t)bz;
 }
 
 __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, const BatchRef& batch,
@@ -217,7 +219,8 @@ __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, con
         }
     }
     if (g.fine_bits > 0)
-        key = (key << g.fine_bits) | (fine_index(in_tile[0], in_tile[1], in_tile[2], g) >> (kFineBitsMax - g.fine_bits));
+        key = (key << g.fine_bits) |
+              (fine_index(in_tile[0], in_tile[1], in_tile[2], g) >> (2 * g.fine_xy_levels + g.fine_z_bits - g.fine_bits));
     return key;
 }
 

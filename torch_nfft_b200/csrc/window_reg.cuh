@@ -26,8 +26,8 @@ namespace nfftb200 {
 //   memory (row pitch P0 floats, planes 128-byte aligned: Geom::sY = P0, sZ = roundup(P0 * P1, 32)).
 // * spread: a finished plane pair of the shared-memory tile is ADDED into the grid by the TMA unit
 //   (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG) as soon as the last warp has added into it, while the
-//   warps go on sweeping: no register staging, no LSU traffic, no flush phase after the sweep.  Out-of-range
-//   box elements are not written, so the periodic wrap is one more box at (x -+ M, y -+ M).
+//   warps go on sweeping: no register staging, no LSU traffic, no flush phase after the sweep.  Tiles that
+//   cross the periodic boundary in X or Y keep the vector-reduction flush (negative box coordinates fault).
 // * gather: the tile's planes are LOADED by the TMA unit (UTMALDG) into the shared-memory tile, completion on
 //   an mbarrier, while the CTA buckets its points.  Out-of-range elements of a load are zero-FILLED, which
 //   would overwrite the other half of a wrapped plane, so tiles that cross the grid boundary in X or Y (2 of
@@ -478,13 +478,14 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
 // - equal POINT ranges of it, so that one heavy column (or a single heavy supercell) is swept by several warps;
 // every unit adds its own partial register blocks into the tile.  Unit = col | lo << 8 | hi << 20 (positions
 // [lo, hi) of the bucketed point list, all inside the column); s_units[rank] is ordered longest first (LPT),
-// *s_nunits counts the units (<= 64) and must have been zeroed before the caller's last barrier.
+// *s_nunits counts the units (<= kRegMaxUnits) and must have been zeroed before the caller's last barrier.
 #ifndef NFFT_REG_SPLIT
 #define NFFT_REG_SPLIT 1
 #endif
 #ifndef NFFT_REG_UNITS
 #define NFFT_REG_UNITS (2 * kRegWarps)  // units a chunk is cut into when its columns are uneven
 #endif
+constexpr int kRegMaxUnits = 128;  // >= NFFT_REG_UNITS + columns of a tile (16 with 4 x 4, 64 with 2 x 2 supercells)
 static_assert(kRegMaxPts < 4096, "unit encoding: 12 bits per point position");
 static_assert(kRegMaxPts % 16 == 0, "the tap windows behind the u8 offsets must stay 16-byte aligned");
 // s_expect (spread with the TMA flush, else nullptr): s_expect[p] = number of units that will add into plane
@@ -492,9 +493,9 @@ static_assert(kRegMaxPts % 16 == 0, "the tap windows behind the u8 offsets must 
 // pairs s0 * sp .. min(s1 * sp + zp, npairs) - 1, each exactly once (see advance() in the spread kernel).
 __device__ __forceinline__ void make_units(const int* s_start, int ncols, int nsz, int* s_units, int* s_nunits,
                                            int* s_expect = nullptr, int sp = 0, int zp = 0, int npairs = 0) {
-    __shared__ int s_raw[64], s_rawcnt[64];
+    __shared__ int s_raw[kRegMaxUnits], s_rawcnt[kRegMaxUnits];
     const int total = s_start[ncols * nsz] - s_start[0];
-    const int maxseg = NFFT_REG_SPLIT && ncols <= 32 ? 16 : 1;  // sum of segments <= NFFT_REG_UNITS + ncols <= 64
+    const int maxseg = NFFT_REG_SPLIT && ncols <= 64 ? 16 : 1;  // sum of segments <= NFFT_REG_UNITS + ncols <= 80
     if ((int)threadIdx.x < ncols) {
         const int c0 = threadIdx.x * nsz;
         const int lo = s_start[c0], cnt = s_start[c0 + nsz] - lo;
@@ -595,9 +596,11 @@ __device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, in
     __syncwarp();
 }
 
-// bisect aid (-DNFFT_REG_OLD_STAGE=1): the previous tap staging through generic pointers
+// The tap staging through generic pointers is the default: the variant above (opaque shared addresses, 22 fewer
+// instructions per round) measured SLOWER on the B200 (c4: spread 4.08 vs 4.04 ms, gather 3.35 vs 3.29 ms,
+// profiles/r02d_ab.txt) -- its volatile accesses pin the order of the loads and stores of a round.
 #ifndef NFFT_REG_OLD_STAGE
-#define NFFT_REG_OLD_STAGE 0
+#define NFFT_REG_OLD_STAGE 1
 #endif
 template <typename Cfg, int LC, bool SCALE_Z = false>
 __device__ __forceinline__ void stage_windows_generic(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
@@ -664,13 +667,16 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     __shared__ int s_expect[32], s_done[32], s_tma[kTmaParamWords];
     const int npairs = (g.P[2] + 1) / 2;
     if (threadIdx.x < 32) s_expect[threadIdx.x] = 0, s_done[threadIdx.x] = 0;
-    if (a.use_tma && threadIdx.x == 0) {
-        // box origins of the tile; a tile that crosses the periodic boundary is added a second time, shifted by
-        // -+ M (out-of-range box elements are not written)
+    // Only tiles that lie inside the grid in X and Y: a box with a NEGATIVE start coordinate raises "illegal
+    // instruction" in cp.reduce.async.bulk.tensor on this driver (scripts/micro/tma_probe.cu test 2,
+    // profiles/r02d_tma_probe.txt), so the 2 of 16 tile rows per dimension that cross the periodic boundary keep
+    // the vector-reduction flush after the sweep.  The Z wrap is per plane and free.
+    const bool tma_tile = a.use_tma && t.org[0] >= 0 && t.org[0] + g.P[0] <= g.M && t.org[1] >= 0 && t.org[1] + g.P[1] <= g.M;
+    if (tma_tile && threadIdx.x == 0) {
         s_tma[0] = t.org[0];
         s_tma[1] = t.org[1];
-        s_tma[2] = t.org[0] < 0 ? g.M : (t.org[0] + g.P[0] > g.M ? -g.M : 0);
-        s_tma[3] = t.org[1] < 0 ? g.M : (t.org[1] + g.P[1] > g.M ? -g.M : 0);
+        s_tma[2] = 0;  // (second box of a wrapped tile: unused, see above)
+        s_tma[3] = 0;
         s_tma[4] = t.org[2];
         s_tma[5] = t.b * g.C + a.k0;
     }
@@ -688,14 +694,14 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     for (int i = threadIdx.x; i < (g.tile_elems >> 2); i += kRegThreads)  // tile_elems is a multiple of 4
         reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    __shared__ int s_order[64], s_nunits;
+    __shared__ int s_order[kRegMaxUnits], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     __syncthreads();
     NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, a.use_tma ? s_expect : nullptr, SP, ZP, npairs);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, tma_tile ? s_expect : nullptr, SP, ZP, npairs);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(0, 5, ph0, pha);
     NFFT_PHASE_ADD(0, 6, pha, phb);
@@ -802,7 +808,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                         // the unit that completes a plane pair hands it to the TMA unit (no other warp will touch
                         // it again); the sweep goes on while the reduction drains
                         const int pr = scz * SP + kp;
-                        if (a.use_tma && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr])
+                        if (tma_tile && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr])
                             tma_flush_plane_pair(&tmap, (uint32_t)__cvta_generic_to_shared(tile), s_tma, pr, g.P[2], g.sZ,
                                                  g.M);
                     }
@@ -880,7 +886,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     }
     NFFT_PHASE_WARP(0, ph1);
     NFFT_PHASE_MARK(ph2);
-    if (a.use_tma) {
+    if (tma_tile) {
         // every plane pair has been handed to the TMA unit by the unit that completed it; the shared memory
         // must stay allocated until the reductions this lane issued have read it
         if (lane == 0) bulk_wait_read_all();
@@ -935,7 +941,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     __shared__ int s_next;
 
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    __shared__ int s_order[64], s_nunits;
+    __shared__ int s_order[kRegMaxUnits], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     // stage the padded tile (periodic wrap resolved per quad)
     // the tile travels with asynchronous copies while the points are loaded and bucketed (both phases

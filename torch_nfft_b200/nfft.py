@@ -119,7 +119,7 @@ def _ptr(t):
 # persistent point plan (the reference recomputes its per-point scratch in
 # every call, core_cuda.cu:188-211, 461-484)
 # --------------------------------------------------------------------------------------
-_TILING_FIELDS = ("dim", "M", "Tx", "Ty", "Tz", "ntx", "nty", "ntz", "pmax", "fine_bits")
+_TILING_FIELDS = ("dim", "M", "Tx", "Ty", "Tz", "ntx", "nty", "ntz", "pmax", "fine_bits", "scx", "scy", "scz")
 
 
 class NfftPlan:
