@@ -21,9 +21,12 @@ coeffs = T.gaussian_interpolated_coeffs(0.1, 3, 64)
 def step():
     return D.nfft_fastsum_point_sharded(x, coeffs, pos, cutoff=4, batch_size=1)
 
+from torch_nfft_b200 import _lib
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+_lib.profile_enable(True)
+_lib.profile_read()
 if world > 1:
     dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,7 +39,9 @@ torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+prof = _lib.profile_read()
 if rank == 0:
+    print("   stages (ms per product):", {k: round(v[0] / K, 3) for k, v in prof.items() if v[1]})
     print(f"c5 fastsum n=2^{n_total.bit_length()-1} on {world} GPU(s): {ms.item():.3f} ms per product, "
           f"{n_total / (ms.item() * 1e-3):.3e} points/s")
 if world > 1:

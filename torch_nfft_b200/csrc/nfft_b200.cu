@@ -282,7 +282,7 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
 
     long long pm = n_points / (sm_count() * 8);
     g.pmax = (int)(pm < 256 ? 256 : (pm > 2048 ? 2048 : pm));
-    if (g.use_reg == 1) g.pmax = kRegMaxPts;
+    if (g.use_reg == 1) g.pmax = kRegMaxPts * kRegBatches;  // a work item = up to kRegBatches batches of the point buffer
     if (g.use_reg == 2) g.pmax = kReg2MaxPts;
     if (g.use_reg == 3) {
         pm = n_points / (sm_count() * 4);
@@ -864,20 +864,6 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
 }
 
 void nfftb200_debug_force_int64(int on) { g_force_int64.store(on ? 1 : 0); }
-
-#ifdef NFFT_PHASE_TIMING
-// debug build only: out[2][24] = accumulated clock64() phase lengths of the register-stencil kernels
-// (window_reg.cuh); reset = 1 clears the counters afterwards
-int nfftb200_debug_phase_read(unsigned long long* out, int reset) {
-    cudaDeviceSynchronize();
-    if (cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 48) != cudaSuccess) return 1;
-    if (reset) {
-        unsigned long long z[48] = {0};
-        cudaMemcpyToSymbol(g_phase, z, sizeof(z));
-    }
-    return 0;
-}
-#endif
 
 void nfftb200_profile_enable(int on) {
     std::lock_guard<std::mutex> lock(g_prof_mutex);
