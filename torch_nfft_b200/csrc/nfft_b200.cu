@@ -248,8 +248,8 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     //   per lane, 24 instead of 36 FFMA2 per point); its add-outs, 4x as frequent per cell, are amortised over
     //   the many points of a supercell.  Everything else uses 4 x 4 x 2.
     // * Fine key bits (sort.cuh: fine_index): the bits that fit the radix passes the tile key needs anyway are
-    //   free; a dense set gets all of them even if that adds a pass, because its tiles are cut into many chunks
-    //   and compact chunks are what lets the points of a chunk share register blocks.
+    //   free; a dense set gets at least 4 of them even if that adds a pass, because its tiles are cut into many
+    //   chunks and compact chunks are what lets the points of a chunk share register blocks.
     g.fine_bits = g.fine_xy_levels = g.fine_z_bits = 0;
     g.sc[0] = g.sc[1] = g.sc[2] = 1;
     static const bool no_fine = getenv("NFFTB200_NO_FINE_SORT") != nullptr;
@@ -268,7 +268,10 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
             int tile_bits = 0;
             while ((1ll << tile_bits) < (long long)g.tiles_per_batch * B) ++tile_bits;
             const int spare = (tile_bits + 7) / 8 * 8 - tile_bits;
-            int k = dense ? total : (spare < total ? spare : total);
+            int k = spare < total ? spare : total;
+            // a dense set whose tile key leaves fewer than 4 spare bits pays one more radix pass for compact chunks
+            // (c5: 9 tile bits, 7 spare: its 2^26-point sort costs 2.6 ms per pass, profiles/r02f_c5.txt)
+            if (dense && k < 4) k = spare + 8 < total ? spare + 8 : total;
             if (tile_bits == 0 && !dense) k = 0;  // a single tile and few points: no radix pass at all
             if (k > 31 - tile_bits) k = 31 - tile_bits;
             g.fine_bits = k < 0 ? 0 : k;
@@ -282,7 +285,7 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
 
     long long pm = n_points / (sm_count() * 8);
     g.pmax = (int)(pm < 256 ? 256 : (pm > 2048 ? 2048 : pm));
-    if (g.use_reg == 1) g.pmax = kRegMaxPts * kRegBatches;  // a work item = up to kRegBatches batches of the point buffer
+    if (g.use_reg == 1) g.pmax = kRegMaxPts;
     if (g.use_reg == 2) g.pmax = kReg2MaxPts;
     if (g.use_reg == 3) {
         pm = n_points / (sm_count() * 4);
@@ -864,6 +867,20 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
 }
 
 void nfftb200_debug_force_int64(int on) { g_force_int64.store(on ? 1 : 0); }
+
+#ifdef NFFT_PHASE_TIMING
+// debug build only: out[2][24] = accumulated clock64() phase lengths of the register-stencil kernels
+// (window_reg.cuh); reset = 1 clears the counters afterwards
+int nfftb200_debug_phase_read(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 48) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[48] = {0};
+        cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 void nfftb200_profile_enable(int on) {
     std::lock_guard<std::mutex> lock(g_prof_mutex);

@@ -109,11 +109,7 @@ constexpr int kRegWarps = kRegThreads / 32;
 #ifndef NFFT_REG_MAXPTS
 #define NFFT_REG_MAXPTS 1536
 #endif
-constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points held in shared memory at a time (one batch of a work item)
-#ifndef NFFT_REG_BATCHES
-#define NFFT_REG_BATCHES 4
-#endif
-constexpr int kRegBatches = NFFT_REG_BATCHES;  // a work item (chunk of a tile's points) is at most this many batches
+constexpr int kRegMaxPts = NFFT_REG_MAXPTS;  // points per work item (chunk) held in shared memory
 #ifndef NFFT_REG_GROUP
 #define NFFT_REG_GROUP 8
 #endif
@@ -135,6 +131,40 @@ static_assert(kRegSX <= 4 && kRegSY <= 4 && kRegSZ <= 4, "cell offsets inside a 
 constexpr int kRegGroup = NFFT_REG_GROUP;  // points staged per warp round: one lane per (point, dimension), 3 * 8 <= 32
 static_assert(kRegGroup == 8, "the sweeps have one point body per slot of an 8-point round");
 constexpr int kGatherSlots = 8;  // point slots of a gather round (= kRegGroup)
+
+// Debug build (-DNFFT_PHASE_TIMING): thread 0 of every CTA adds the clock64() length of its phases to
+// g_phase[kernel][phase]; read back through nfftb200_debug_phase_read.  Phases: 0 zero + bucket +
+// order, 1 column sweep (until this warp is done), 2 wait for the other warps, 3 flush / store,
+// 4 number of CTAs.
+#ifdef NFFT_PHASE_TIMING
+__device__ unsigned long long g_phase[2][24];  // [8 + w]: sweep length of warp w
+#define NFFT_PHASE_MARK(var) const long long var = clock64()
+#define NFFT_PHASE_ADD(kern, ph, t0, t1) \
+    if (threadIdx.x == 0) atomicAdd(&g_phase[kern][ph], (unsigned long long)((t1) - (t0)))
+#define NFFT_PHASE_WARP(kern, t0) \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[kern][8 + (threadIdx.x >> 5)], (unsigned long long)(clock64() - (t0)))
+// [16] longest CTA (cycles), [17] / [18] first CTA start / last CTA end (globaltimer ns, [17] stored negated
+// so that a zeroed counter works with atomicMax), [19..22] CTAs by points: <= 1/4, 1/2, 3/4, 1 of kRegMaxPts
+__device__ __forceinline__ unsigned long long phase_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NFFT_PHASE_BEGIN(kern) \
+    if (threadIdx.x == 0) atomicMax(&g_phase[kern][17], ~phase_ns())
+#define NFFT_PHASE_END(kern, t0, t1, cnt)                                                  \
+    if (threadIdx.x == 0) {                                                                \
+        atomicMax(&g_phase[kern][16], (unsigned long long)((t1) - (t0)));                  \
+        atomicMax(&g_phase[kern][18], phase_ns());                                         \
+        atomicAdd(&g_phase[kern][19 + min(3, (int)((cnt) * 4 / (kRegMaxPts + 1)))], 1ull); \
+    }
+#else
+#define NFFT_PHASE_MARK(var)
+#define NFFT_PHASE_ADD(kern, ph, t0, t1)
+#define NFFT_PHASE_WARP(kern, t0)
+#define NFFT_PHASE_BEGIN(kern)
+#define NFFT_PHASE_END(kern, t0, t1, cnt)
+#endif
 
 template <int LC, int SX, int SY, int SZ>
 struct RegCfg {
@@ -469,8 +499,7 @@ __device__ __forceinline__ void make_units(const int* s_start, int ncols, int ns
     if ((int)threadIdx.x < ncols) {
         const int c0 = threadIdx.x * nsz;
         const int lo = s_start[c0], cnt = s_start[c0 + nsz] - lo;
-        // cnt / share rounded at 0.75: a column is cut in two from 1.75x its share of the batch on
-        int nseg = (int)(((long long)cnt * NFFT_REG_UNITS + total / 4) / (total > 0 ? total : 1));
+        int nseg = (int)(((long long)cnt * NFFT_REG_UNITS + total / 2) / (total > 0 ? total : 1));  // round(cnt / share)
         nseg = nseg < 1 ? 1 : (nseg > maxseg ? maxseg : nseg);
         if (cnt < 2 * kRegGroup * nseg) nseg = cnt / (2 * kRegGroup) > 0 ? cnt / (2 * kRegGroup) : 1;  // >= 2 rounds each
         for (int j = 0; j < nseg && cnt > 0; ++j) {
@@ -628,15 +657,16 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     extern __shared__ __align__(128) float smem_reg[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
+    NFFT_PHASE_MARK(ph0);
+    NFFT_PHASE_BEGIN(0);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
     float* tile = align_tile(smem_reg);
     // TMA flush: plane pairs leave for the grid as soon as every unit that adds into them has done so
-    __shared__ int s_expect[32], s_done[32], s_tma[kTmaParamWords], s_boff;
+    __shared__ int s_expect[32], s_done[32], s_tma[kTmaParamWords];
     const int npairs = (g.P[2] + 1) / 2;
     if (threadIdx.x < 32) s_expect[threadIdx.x] = 0, s_done[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_boff = 0;
     // Only tiles that lie inside the grid in X and Y: a box with a NEGATIVE start coordinate raises "illegal
     // instruction" in cp.reduce.async.bulk.tensor on this driver (scripts/micro/tma_probe.cu test 2,
     // profiles/r02d_tma_probe.txt), so the 2 of 16 tile rows per dimension that cross the periodic boundary keep
@@ -667,28 +697,16 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     __shared__ int s_order[kRegMaxUnits], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     __syncthreads();
-    // A work item holds up to kRegBatches * kRegMaxPts points (heavy tiles of clustered / dense point sets): they
-    // pass through the shared-memory point buffer in batches while the tile stays, so that the tile's zeroing and
-    // flush -- the fixed costs of a work item -- are paid once per item, not once per kRegMaxPts points.  The
-    // batch state lives in shared memory and the item is re-read per batch: registers are what the sweep lacks.
-    const bool single_batch = (int)(t.p_hi - t.p_lo) <= kRegMaxPts;
-    // plane pairs leave progressively only if no later batch adds into them again
-    const bool progressive = tma_tile && single_batch;
-    for (;;) {
-    {
-        const uint4 item = __ldg(a.items + blockIdx.x);
-        const int cnt_total = (int)(item.z - item.y);
-        const int nbatch = (cnt_total + kRegMaxPts - 1) / kRegMaxPts;
-        const int per_batch = (cnt_total + nbatch - 1) / nbatch;
-        const int boff = s_boff;
-        const int cnt = cnt_total - boff < per_batch ? cnt_total - boff : per_batch;
-        TileCtx tb = t;
-        tb.p_lo = (long long)item.y + boff;
-        bucket_points<SX, SY, SZ, true>(g, a, tb, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
-        if (threadIdx.x == 0) s_boff = boff + cnt;  // read again only after the barriers that end this batch
-    }
-    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, progressive ? s_expect : nullptr, SP, ZP, npairs);
-    // (per-lane constants of the sweep: set up after the bucketing, which needs the registers for the point records)
+    NFFT_PHASE_MARK(pha);
+    const int cnt = (int)(t.p_hi - t.p_lo);
+    bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    NFFT_PHASE_MARK(phb);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, tma_tile ? s_expect : nullptr, SP, ZP, npairs);
+    NFFT_PHASE_MARK(ph1);
+    NFFT_PHASE_ADD(0, 5, ph0, pha);
+    NFFT_PHASE_ADD(0, 6, pha, phb);
+    NFFT_PHASE_ADD(0, 7, phb, ph1);
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = s_win + warp * Cfg::WIN_FLOATS;
     constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;  // z windows start here
@@ -712,7 +730,6 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     uint32_t awi[CPL], awj[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
-
 
     // work units (columns of supercells or z-ranges of heavy columns) are handed out dynamically
     const int nunits = s_nunits;
@@ -791,7 +808,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                         // the unit that completes a plane pair hands it to the TMA unit (no other warp will touch
                         // it again); the sweep goes on while the reduction drains
                         const int pr = scz * SP + kp;
-                        if (progressive && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr])
+                        if (tma_tile && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr])
                             tma_flush_plane_pair(&tmap, (uint32_t)__cvta_generic_to_shared(tile), s_tma, pr, g.P[2], g.sZ,
                                                  g.M);
                     }
@@ -867,32 +884,16 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
             advance(scz, true);
         }
     }
-    if (single_batch) break;
-    __syncthreads();  // every warp has finished the batch: the point buffer and the bucket tables are free
-    {
-        const uint4 item = __ldg(a.items + blockIdx.x);
-        if (s_boff >= (int)(item.z - item.y)) break;  // (uniform: s_boff was written before the barrier above)
-    }
-    for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
-    __syncthreads();
-    }  // batches
-    if (progressive) {
+    NFFT_PHASE_WARP(0, ph1);
+    NFFT_PHASE_MARK(ph2);
+    if (tma_tile) {
         // every plane pair has been handed to the TMA unit by the unit that completed it; the shared memory
         // must stay allocated until the reductions this lane issued have read it
-        if ((threadIdx.x & 31) == 0) bulk_wait_read_all();
+        if (lane == 0) bulk_wait_read_all();
         return;
     }
     __syncthreads();
-    if (tma_tile) {
-        // several batches added into the tile: all its planes leave now, through the TMA unit
-        if (threadIdx.x == 0) {
-            for (int pr = 0; pr < npairs; ++pr)
-                tma_flush_plane_pair(&tmap, (uint32_t)__cvta_generic_to_shared(tile), s_tma, pr, g.P[2], g.sZ, g.M);
-            bulk_wait_read_all();
-        }
-        return;
-    }
+    NFFT_PHASE_MARK(ph3);
 
     // flush: vector reductions into the global grid; untouched (== 0) quads are skipped
     for_each_quad3_rows(g, t, [&](int so, long long cell) {
@@ -900,6 +901,13 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
         const float4 val = make_float4(s[0], s[1], s[2], s[3]);
         if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) reduce_quad(g, a.grid, t.b, a.k0, cell, val);
     });
+    NFFT_PHASE_MARK(ph4);
+    NFFT_PHASE_ADD(0, 0, ph0, ph1);
+    NFFT_PHASE_ADD(0, 1, ph1, ph2);
+    NFFT_PHASE_ADD(0, 2, ph2, ph3);
+    NFFT_PHASE_ADD(0, 3, ph3, ph4);
+    NFFT_PHASE_ADD(0, 4, 0, 1);
+    NFFT_PHASE_END(0, ph0, ph4, cnt);
 }
 
 // ======================================================================================
@@ -913,13 +921,13 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     extern __shared__ __align__(128) float smem_reg[];
     TileCtx t;
     if (!decode_item(g, a, t)) return;
+    NFFT_PHASE_MARK(ph0);
+    NFFT_PHASE_BEGIN(1);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
     float* tile = align_tile(smem_reg);
     __shared__ __align__(8) unsigned long long s_mbar;
-    __shared__ int s_boff;
-    if (threadIdx.x == 0) s_boff = 0;
     // planes by TMA unless the tile crosses the periodic boundary in X or Y (a load zero-fills out-of-range
     // elements, which would overwrite the wrapped half; the Z wrap is per plane)
     const bool tma_tile = a.use_tma && t.org[0] >= 0 && t.org[0] + g.P[0] <= g.M && t.org[1] >= 0 && t.org[1] + g.P[1] <= g.M;
@@ -969,32 +977,22 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
         });
     }
     __syncthreads();
-    // the points of the work item pass through the point buffer in batches while the tile stays (see the spread)
-    const bool single_batch = (int)(t.p_hi - t.p_lo) <= kRegMaxPts;
-    for (;;) {
-    int boff;
-    {
-        const uint4 item = __ldg(a.items + blockIdx.x);
-        const int cnt_total = (int)(item.z - item.y);
-        const int nbatch = (cnt_total + kRegMaxPts - 1) / kRegMaxPts;
-        const int per_batch = (cnt_total + nbatch - 1) / nbatch;
-        boff = s_boff;
-        const int cnt = cnt_total - boff < per_batch ? cnt_total - boff : per_batch;
-        TileCtx tb = t;
-        tb.p_lo = (long long)item.y + boff;
-        bucket_points<SX, SY, SZ, false>(g, a, tb, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
-        if (threadIdx.x == 0) s_boff = boff + cnt;  // read again only after the barriers that end this batch
-    }
-    if (boff == 0) {
-        if (tma_tile) {
-            // every thread observes the completion itself (the mbarrier makes the TMA writes visible to its waiters)
-            if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0) && a.flags) atomicAdd(a.flags + 1, 1u);
-        } else {
-            cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
-        }
+    NFFT_PHASE_MARK(pha);
+    const int cnt = (int)(t.p_hi - t.p_lo);
+    bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    NFFT_PHASE_MARK(phb);
+    if (tma_tile) {
+        // every thread observes the completion itself (the mbarrier makes the TMA writes visible to its waiters)
+        if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0) && a.flags) atomicAdd(a.flags + 1, 1u);
+    } else {
+        cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
     }
     make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
-    // (per-lane constants of the sweep: set up after the bucketing, which needs the registers for the point records)
+    NFFT_PHASE_MARK(ph1);
+    NFFT_PHASE_ADD(1, 5, ph0, pha);
+    NFFT_PHASE_ADD(1, 6, pha, phb);
+    NFFT_PHASE_ADD(1, 7, phb, ph1);
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = s_win + warp * Cfg::WIN_FLOATS;
     constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;  // z windows start here
@@ -1018,7 +1016,6 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     for (int q = 0; q < CPL; ++q) awi[q] = wbase + 4u * wi[q], awj[q] = wbase + 4u * wj[q];
     // planes above the padded tile are never weighted (their taps are zero) but must stay in bounds
     const int zmax = g.P[2] - 1;
-
 
     const int nunits = s_nunits;
     for (;;) {
@@ -1141,17 +1138,18 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
             __syncwarp();
         }
     }
-    if (single_batch) break;
-    __syncthreads();  // every warp has finished the batch
-    {
-        const uint4 item = __ldg(a.items + blockIdx.x);
-        if (s_boff >= (int)(item.z - item.y)) break;
-    }
-    for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
-    __syncthreads();
-    }  // batches
     (void)WZ;
+    NFFT_PHASE_WARP(1, ph1);
+    NFFT_PHASE_MARK(ph2);
+#ifdef NFFT_PHASE_TIMING
+    __syncthreads();
+#endif
+    NFFT_PHASE_MARK(ph3);
+    NFFT_PHASE_ADD(1, 0, ph0, ph1);
+    NFFT_PHASE_ADD(1, 1, ph1, ph2);
+    NFFT_PHASE_ADD(1, 2, ph2, ph3);
+    NFFT_PHASE_ADD(1, 4, 0, 1);
+    NFFT_PHASE_END(1, ph0, ph3, cnt);
 }
 
 }  // namespace nfftb200
