@@ -308,8 +308,9 @@ def strong_c4(torch, dist, T, D, dev, rank, world, steps):
             return T.nfft_forward(y, plan=plan, m=m, real_output=True)
     else:
         def step():
-            y = D.nfft_adjoint_point_sharded(x, pos, None, N, m, batch_size=1, group=group)
-            return D.nfft_forward_point_sharded(y, pos, None, m, True, batch_size=1, group=group)
+            plan = T.NfftPlan(pos)  # this rank's slice is binned once per step, for its spread and its gather
+            y = D.nfft_adjoint_point_sharded(x, pos, None, N, m, batch_size=1, group=group, plan=plan)
+            return D.nfft_forward_point_sharded(y, pos, None, m, True, batch_size=1, group=group, plan=plan)
     ms = timed_max(torch, dist, dev, step, steps, 3, world)
     out = {"workload": "c4: 3D N=128 m=4, 2^24 uniform points in 4 point sets, adjoint+forward", "nranks": world,
            "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "points/s", "scaling": "strong",

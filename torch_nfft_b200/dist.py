@@ -56,14 +56,17 @@ def shard_points(n: int, world: int, rank: int):
 # engines
 # --------------------------------------------------------------------------------------
 class CudaEngine:
-    """Stages of the transform on the current CUDA device through the C ABI."""
+    """Stages of the transform on the current CUDA device through the C ABI.  `plan` (an `NfftPlan` of exactly the
+    `pos` / `batch` passed along) lets spread and gather of the same points share one binning."""
+
+    supports_plans = True
 
     @staticmethod
     def _geom(pos, batch, batch_size):
         pos, batch, n, d, B, _ = _nfft._check_points(pos, batch, batch_size)
         return pos, batch, n, d, B
 
-    def spread(self, x, pos, batch, B, N, m):
+    def spread(self, x, pos, batch, B, N, m, plan=None):
         """x [n, *cols] -> partial grid [B*C, (2N)^d] (float32, or complex64 for complex x)."""
         pos, batch, n, d, B = self._geom(pos, batch, B)
         x = x.contiguous()
@@ -72,10 +75,14 @@ class CudaEngine:
         grid = torch.empty((B * C,) + (2 * N,) * d, dtype=x.dtype, device=pos.device)
         L = _lib.lib()
         with torch.cuda.device(pos.device):
+            pbuf = None
+            if plan is not None and n > 0:
+                pbuf = plan._sorted(N, m, C, flags)
+                flags |= _lib.PLANNED
             ws = _nfft._workspace(L.nfftb200_workspace_bytes(_lib.OP_SPREAD, n, 0, d, N, m, B, C, flags), pos.device)
-            _lib.check(L.nfftb200_spread(pos.data_ptr(), x.data_ptr(), _nfft._ptr(batch), 0, 0, grid.data_ptr(), n, d, N,
-                                         m, B, C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(pos.device)),
-                       "spread")
+            _lib.check(L.nfftb200_spread(pos.data_ptr(), x.data_ptr(), _nfft._ptr(batch), _nfft._ptr(pbuf),
+                                         0 if pbuf is None else pbuf.numel(), grid.data_ptr(), n, d, N, m, B, C, flags,
+                                         ws.data_ptr(), ws.numel(), _nfft._stream_ptr(pos.device)), "spread")
         return grid
 
     def adjoint_finish(self, grid, d, B, cols, N, m, real_output):
@@ -104,7 +111,7 @@ class CudaEngine:
                                                 ws.numel(), _nfft._stream_ptr(xhat.device)), "forward_begin")
         return grid
 
-    def gather(self, grid, pos, batch, B, cols, N, m):
+    def gather(self, grid, pos, batch, B, cols, N, m, plan=None):
         pos, batch, n, d, B = self._geom(pos, batch, B)
         C = grid.shape[0] // B
         flags = _lib.X_COMPLEX if grid.is_complex() else 0
@@ -113,9 +120,14 @@ class CudaEngine:
             return y
         L = _lib.lib()
         with torch.cuda.device(grid.device):
+            pbuf = None
+            if plan is not None:
+                pbuf = plan._sorted(N, m, C, flags)
+                flags |= _lib.PLANNED
             ws = _nfft._workspace(L.nfftb200_workspace_bytes(_lib.OP_GATHER, 0, n, d, N, m, B, C, flags), grid.device)
-            _lib.check(L.nfftb200_gather(pos.data_ptr(), _nfft._ptr(batch), 0, 0, grid.data_ptr(), y.data_ptr(), n, d, N, m,
-                                         B, C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(grid.device)), "gather")
+            _lib.check(L.nfftb200_gather(pos.data_ptr(), _nfft._ptr(batch), _nfft._ptr(pbuf),
+                                         0 if pbuf is None else pbuf.numel(), grid.data_ptr(), y.data_ptr(), n, d, N, m, B,
+                                         C, flags, ws.data_ptr(), ws.numel(), _nfft._stream_ptr(grid.device)), "gather")
         return y
 
     def fastsum_middle(self, grid, coeffs, d, B, N, m):
@@ -172,8 +184,15 @@ def _all_gather_batches(y_local, group):
 # --------------------------------------------------------------------------------------
 # point-sharded transforms: every rank passes ITS slice of the points
 # --------------------------------------------------------------------------------------
+def _local_plan(eng, pos, batch, B, plan):
+    """The binning of this rank's point slice: the caller's, or (for engines that take plans) a fresh one."""
+    if not getattr(eng, "supports_plans", False):
+        return None
+    return plan if plan is not None else _nfft.NfftPlan(pos, batch, batch_size=B)
+
+
 def nfft_adjoint_point_sharded(x, pos, batch=None, bandwidth=16, cutoff=3, real_output=False, *, batch_size=None,
-                               group=None, engine=None, scatter_output=False):
+                               group=None, engine=None, scatter_output=False, plan=None):
     """Adjoint NFFT of a point set that is split across ranks.
 
     Every rank spreads its points into a partial oversampled grid.  If the number of batch entries is
@@ -191,7 +210,7 @@ def nfft_adjoint_point_sharded(x, pos, batch=None, bandwidth=16, cutoff=3, real_
     if B is None:
         raise RuntimeError("point-sharded transforms with a batch vector need batch_size= (the global value)")
     cols = tuple(x.shape[1:])
-    grid = eng.spread(x, pos, batch, B, bandwidth, cutoff)
+    grid = eng.spread(x, pos, batch, B, bandwidth, cutoff, **({"plan": plan} if plan is not None else {}))
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1 and B % world == 0:
         rank = dist.get_rank(group)
@@ -209,19 +228,22 @@ def nfft_adjoint_point_sharded(x, pos, batch=None, bandwidth=16, cutoff=3, real_
 
 
 def nfft_forward_point_sharded(xhat, pos, batch=None, cutoff=3, real_output=False, *, batch_size=None, group=None,
-                               engine=None):
-    """Forward NFFT at this rank's slice of the points; xhat is replicated.  Returns [n_local, *cols]."""
+                               engine=None, plan=None):
+    """Forward NFFT at this rank's slice of the points; xhat is replicated.  Returns [n_local, *cols].
+    `plan`: the NfftPlan of this rank's slice (e.g. the one the adjoint of the same points used)."""
     eng = engine or _default_engine
     d = pos.shape[1]
     B, N = xhat.shape[0], xhat.shape[1]
     grid = eng.forward_begin(xhat, d, cutoff, real_output)
-    return eng.gather(grid, pos, batch, B, tuple(xhat.shape[1 + d:]), N, cutoff)
+    return eng.gather(grid, pos, batch, B, tuple(xhat.shape[1 + d:]), N, cutoff,
+                      **({"plan": plan} if plan is not None else {}))
 
 
 def nfft_fastsum_point_sharded(x, coeffs, sources, targets=None, source_batch=None, target_batch=None, *,
-                               cutoff=3, batch_size=None, group=None, engine=None):
+                               cutoff=3, batch_size=None, group=None, engine=None, source_plan=None, target_plan=None):
     """Fastsum with sources and targets split across ranks (each rank passes its slices of both).
-    One all-reduce of the oversampled grid; the result rows stay sharded like `targets`."""
+    One all-reduce of the oversampled grid; the result rows stay sharded like `targets`.
+    `source_plan` / `target_plan`: NfftPlans of this rank's slices, kept by callers that multiply repeatedly."""
     eng = engine or _default_engine
     if targets is None:
         targets, target_batch = sources, source_batch
@@ -230,10 +252,15 @@ def nfft_fastsum_point_sharded(x, coeffs, sources, targets=None, source_batch=No
     B = int(batch_size) if batch_size is not None else (1 if source_batch is None else None)
     if B is None:
         raise RuntimeError("point-sharded transforms with a batch vector need batch_size= (the global value)")
-    grid = eng.spread(x, sources, source_batch, B, N, cutoff)
+    # the symmetric product spreads from and gathers at the same points: one binning serves both stages
+    symmetric = targets is sources and target_batch is source_batch
+    src_plan = _local_plan(eng, sources, source_batch, B, source_plan) if (symmetric or source_plan is not None) else None
+    tgt_plan = src_plan if symmetric else target_plan
+    grid = eng.spread(x, sources, source_batch, B, N, cutoff, **({"plan": src_plan} if src_plan is not None else {}))
     grid = _sum_over_ranks(grid, group)
     grid = eng.fastsum_middle(grid, coeffs, d, B, N, cutoff)
-    return eng.gather(grid, targets, target_batch, B, tuple(x.shape[1:]), N, cutoff)
+    return eng.gather(grid, targets, target_batch, B, tuple(x.shape[1:]), N, cutoff,
+                      **({"plan": tgt_plan} if tgt_plan is not None else {}))
 
 
 # --------------------------------------------------------------------------------------
