@@ -13,6 +13,8 @@
 
 namespace nfftb200 {
 
+constexpr int kPlanFlagWords = 8;  // plan flags: [0] points dropped by a window kernel (stale plan), [1] TMA timeouts
+
 // ------------------------------------------------------------------------- block scan helpers
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const int lane = threadIdx.x & 31;
@@ -424,9 +426,10 @@ fill_items_kernel(const uint32_t* __restrict__ bin_start, const uint32_t* __rest
 __global__ void __launch_bounds__(kRsBins)
 finish_single_pass_kernel(const uint32_t* __restrict__ table_scanned, int nblocks, int nbins, uint32_t n, int pmax,
                           uint32_t* __restrict__ bin_start, uint32_t* __restrict__ chunk_start,
-                          uint4* __restrict__ items) {
+                          uint4* __restrict__ items, long long max_items, uint32_t* __restrict__ flags) {
     __shared__ uint32_t s_warp[33];
     const int b = threadIdx.x;
+    if (b < kPlanFlagWords) flags[b] = 0;  // (this launch also stands in for the memsets of the general path)
     uint32_t lo = 0, hi = 0;
     if (b < nbins) {
         lo = table_scanned[(long long)b * nblocks];
@@ -445,6 +448,8 @@ finish_single_pass_kernel(const uint32_t* __restrict__ table_scanned, int nblock
             items[first + c] = make_uint4((uint32_t)b, lo + (uint32_t)((unsigned long long)cnt * c / nch),
                                           lo + (uint32_t)((unsigned long long)cnt * (c + 1) / nch), 0u);
     }
+    // entries beyond the last work item: empty ranges (the window kernels are launched over max_items CTAs)
+    for (long long w = (long long)total + b; w < max_items; w += kRsBins) items[w] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------------- host orchestration
@@ -460,7 +465,6 @@ struct SortLayout {   // transient scratch
     size_t keys0, keysA, keysB, idxT, bin_count, nch, table, scan, total;
     long long nblocks;
 };
-constexpr int kPlanFlagWords = 8;  // flags[0]: points dropped by a window kernel (stale plan), see PlanFlags
 
 inline PlanLayout plan_layout(long long n, const Geom& g) {
     PlanLayout L{};
@@ -551,8 +555,12 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
     uint32_t* scan = (uint32_t*)(scratch + L.scan);
     const BatchRef bref{batch, batch_is_offsets ? g.B : 0};
 
-    NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, st));
-    NF_CUDA(cudaMemsetAsync(plan->flags, 0, kPlanFlagWords * 4, st));
+    // single radix pass whose digit is the bin (small problems): one finishing launch, no memsets
+    const bool single_pass = n > 0 && passes == 1 && g.fine_bits == 0 && nbins <= kRsBins;
+    if (!single_pass) {
+        NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, st));
+        NF_CUDA(cudaMemsetAsync(plan->flags, 0, kPlanFlagWords * 4, st));
+    }
     // stable LSD radix sort of (key, index) over the key bits that can be set
     const uint32_t* kin = keys0;
     const uint32_t* iin = nullptr;  // identity payload on the first pass
@@ -577,11 +585,10 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
             kin = kout;
             iin = iout;
         }
-        if (passes == 1 && g.fine_bits == 0 && nbins <= kRsBins) {
+        if (single_pass) {
             // the digit is the bin: everything after the scatter in one small launch
-            NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)plan->max_items * sizeof(uint4), st));
             NF_LAUNCH(finish_single_pass_kernel, 1, kRsBins, 0, st, table, (int)L.nblocks, (int)nbins, (uint32_t)n,
-                      g.pmax, bin_start, chunk_start, plan->items);
+                      g.pmax, bin_start, chunk_start, plan->items, plan->max_items, plan->flags);
             return NFFTB200_OK;
         }
         if (passes > 0) {
