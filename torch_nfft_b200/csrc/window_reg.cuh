@@ -182,6 +182,21 @@ struct RegCfg {
     //   z windows    : kRegGroup rows of ZWP floats (16-byte aligned rows, read as float4)
     static constexpr int XYP = (WX > WY ? WX : WY) + 1 + (((WX > WY ? WX : WY) + 1) % 2 == 0 ? 1 : 0);
     static constexpr int ZWP = ZQ * 4 + 8;  // 20 floats: rows 16-byte aligned, row starts spread over the banks
+    // Row skipping.  The (x, y) positions c = lane + 32 q of group q = 0 lie in rows 0 .. ROW_FIRST_MAX, those of the
+    // last group in rows ROW_LAST_MIN .. WY-1, and a point whose y offset inside its supercell is oy has taps in rows
+    // [oy, oy + LC) only.  For 4 x 4 x 2 supercells and L = 10 (13 rows: group 0 = rows 0-2, group 5 = row 12) EXACTLY
+    // ONE of the two groups is all zero for every point (oy <= 2: the last, oy = 3: the first), so the point body
+    // exists in two variants of CPL - 1 groups each (30 instead of 36 FFMA2), chosen per point by a warp-uniform
+    // mask the tap staging returns (a warp ballot over the y lanes of the round: no shared-memory round trip in
+    // front of the branch).  Two whole bodies, not guards around one group: ptxas if-converts small guarded blocks
+    // into predicated FFMA2s that still issue.
+    static constexpr int ROW_FIRST_MAX = 31 / WX;
+    static constexpr int ROW_LAST_MIN = (32 * (CPL - 1)) / WX;
+#ifndef NFFT_REG_ROWSKIP
+#define NFFT_REG_ROWSKIP 1
+#endif
+    static constexpr bool ROWSKIP = NFFT_REG_ROWSKIP && CPL > 2 && ROW_FIRST_MAX + 1 == ROW_LAST_MIN - LC + 1 &&
+                                    ROW_FIRST_MAX + 1 == SY - 1;  // oy <= ROW_FIRST_MAX <=> last group empty; else first
     static constexpr int WIN_FLOATS = (2 * kRegGroup * XYP + 3) / 4 * 4 + kRegGroup * ZWP;
 };
 
@@ -551,9 +566,11 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 __device__ __forceinline__ void sts_zero16(uint32_t addr) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "f"(0.f) : "memory");
 }
+// Returns the row-skip mask of the round (RegCfg::ROWSKIP): bit 3 p + 1 set <=> the FIRST position group of point
+// p is all zero (else the last one is); 0 for configurations without row skipping.
 template <typename Cfg, int LC, bool SCALE_Z = false>
-__device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, int base, int npts, uint32_t wbase, int lane,
-                                              bool pow2) {
+__device__ __forceinline__ unsigned stage_windows(const Geom& g, uint32_t pts_sh, int base, int npts, uint32_t wbase,
+                                                  int lane, bool pow2) {
     constexpr int kQuads = Cfg::WIN_FLOATS / 4;
 #pragma unroll
     for (int k = 0; k < (kQuads + 31) / 32; ++k) {
@@ -561,6 +578,7 @@ __device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, in
         if (qd < kQuads) sts_zero16(wbase + 16u * (uint32_t)qd);
     }
     __syncwarp();
+    bool skip_first = false;
     const int pt = lane / 3, api = lane - pt * 3;  // API dim 0,1,2 <-> slot Z,Y,X
     if (pt < npts) {
         const int slot = 2 - api;
@@ -573,6 +591,7 @@ __device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, in
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
         float amp = g.inv_sqrt_b_pi;
         if (SCALE_Z && slot == 2) amp *= lds_at(rec + 12u);
+        skip_first = slot == 1 && off > Cfg::ROW_FIRST_MAX;
         if (pow2) {
             // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
             // rounded, i.e. identical to the reference's double evaluation (:84-86)
@@ -594,6 +613,7 @@ __device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, in
         }
     }
     __syncwarp();
+    return Cfg::ROWSKIP ? __ballot_sync(0xffffffffu, skip_first) : 0u;
 }
 
 // The tap staging through generic pointers is the default: the variant above (opaque shared addresses, 22 fewer
@@ -603,8 +623,8 @@ __device__ __forceinline__ void stage_windows(const Geom& g, uint32_t pts_sh, in
 #define NFFT_REG_OLD_STAGE 1
 #endif
 template <typename Cfg, int LC, bool SCALE_Z = false>
-__device__ __forceinline__ void stage_windows_generic(const Geom& g, const float4* s_pts, const unsigned char* s_off, int base,
-                                              int npts, float* win, int lane, bool pow2) {
+__device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const float4* s_pts, const unsigned char* s_off,
+                                                          int base, int npts, float* win, int lane, bool pow2) {
     constexpr int kQuads = Cfg::WIN_FLOATS / 4;
 #pragma unroll
     for (int k = 0; k < (kQuads + 31) / 32; ++k) {
@@ -612,6 +632,7 @@ __device__ __forceinline__ void stage_windows_generic(const Geom& g, const float
         if (qd < kQuads) reinterpret_cast<float4*>(win)[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
+    bool skip_first = false;
     const int pt = lane / 3, api = lane - pt * 3;  // API dim 0,1,2 <-> slot Z,Y,X
     if (pt < npts) {
         const int slot = 2 - api;
@@ -623,6 +644,7 @@ __device__ __forceinline__ void stage_windows_generic(const Geom& g, const float
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
         float amp = g.inv_sqrt_b_pi;
         if (SCALE_Z && slot == 2) amp *= s_pts[base + pt].w;
+        skip_first = slot == 1 && off > Cfg::ROW_FIRST_MAX;
         if (pow2) {
             // M is a power of two: p*M, its fractional part and frac + (m - l) are exact or correctly
             // rounded, i.e. identical to the reference's double evaluation (:84-86)
@@ -644,6 +666,7 @@ __device__ __forceinline__ void stage_windows_generic(const Geom& g, const float
         }
     }
     __syncwarp();
+    return Cfg::ROWSKIP ? __ballot_sync(0xffffffffu, skip_first) : 0u;
 }
 
 // ======================================================================================
@@ -832,9 +855,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
             for (int base = lo_seg; base < hi_seg; base += kRegGroup) {
                 const int npts = hi_seg - base < kRegGroup ? hi_seg - base : kRegGroup;
 #if NFFT_REG_OLD_STAGE
-                stage_windows_generic<Cfg, LC, true>(g, s_pts, s_off, base, npts, win, lane, pow2);
+                const unsigned skipmask = stage_windows_generic<Cfg, LC, true>(g, s_pts, s_off, base, npts, win, lane, pow2);
 #else
-                stage_windows<Cfg, LC, true>(g, pts_sh, base, npts, wbase, lane, pow2);
+                const unsigned skipmask = stage_windows<Cfg, LC, true>(g, pts_sh, base, npts, wbase, lane, pow2);
 #endif
                 // One copy of the point body per slot of the round (window loads with immediate offsets),
                 // entered through a switch; a slot that ends a supercell leaves the switch so that the ONE
@@ -848,22 +871,39 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                         next_end = s_start[c0 + scz + 1];
                     }
                     const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
-                    auto point = [&](auto kc) {
-                        constexpr int K = decltype(kc)::value;
+                    // groups [Q0, Q1) of the point in slot K; REV: descending (keeps ptxas from merging the two
+                    // row-skip variants back into one body with a predicated group)
+                    auto body = [&](auto kc, auto q0c, auto q1c, auto revc) {
+                        constexpr int K = decltype(kc)::value, Q0 = decltype(q0c)::value, Q1 = decltype(q1c)::value;
+                        constexpr bool REV = decltype(revc)::value != 0;
                         float w0[CPL], w1[CPL];
 #pragma unroll
-                        for (int q = 0; q < CPL; ++q) {
+                        for (int i = Q0; i < Q1; ++i) {
+                            const int q = REV ? Q1 - 1 - (i - Q0) : i;
                             w1[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awj[q]);
                             w0[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awi[q]);
                         }
                         float2 wz[ZP];
                         lds_window<(kXY + K * Cfg::ZWP) * 4, Cfg::ZQ>(wbase, wz);
 #pragma unroll
-                        for (int q = 0; q < CPL; ++q) {
+                        for (int i = Q0; i < Q1; ++i) {
+                            const int q = REV ? Q1 - 1 - (i - Q0) : i;
                             const float v = w1[q] * w0[q];
                             const float2 vv = make_float2(v, v);
 #pragma unroll
                             for (int kp = 0; kp < ZP; ++kp) acc[q][kp] = ffma2(vv, wz[kp], acc[q][kp]);
+                        }
+                    };
+                    auto point = [&](auto kc) {
+                        constexpr int K = decltype(kc)::value;
+                        if constexpr (Cfg::ROWSKIP) {
+                            // warp-uniform (a ballot): set = the first group of this point is all zero, else the last
+                            if (skipmask & (1u << (3 * K + 1)))
+                                body(kc, IntC<1>{}, IntC<CPL>{}, IntC<1>{});
+                            else
+                                body(kc, IntC<0>{}, IntC<CPL - 1>{}, IntC<0>{});
+                        } else {
+                            body(kc, IntC<0>{}, IntC<CPL>{}, IntC<0>{});
                         }
                     };
 #define NFFT_SLOT(K)                                                                       \
@@ -1070,9 +1110,9 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
 #if NFFT_REG_OLD_STAGE
-            stage_windows_generic<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            const unsigned skipmask = stage_windows_generic<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
 #else
-            stage_windows<Cfg, LC>(g, pts_sh, base, npts, wbase, lane, pow2);
+            const unsigned skipmask = stage_windows<Cfg, LC>(g, pts_sh, base, npts, wbase, lane, pow2);
 #endif
             // As in the spread: one copy of the point body per slot (window loads with immediate offsets, the
             // partial sum in a static register), entered through a switch; a slot that ends a supercell
@@ -1089,11 +1129,14 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                     next_end = s_start[c0 + scz + 1];
                 }
                 const int stop = npts < next_end - base ? npts : next_end - base;  // slots gp .. stop-1: supercell scz
-                auto gpoint = [&](auto kc) {
-                    constexpr int K = decltype(kc)::value;
+                // groups [Q0, Q1) of the point in slot K (see the spread kernel: row skipping)
+                auto gbody = [&](auto kc, auto q0c, auto q1c, auto revc) {
+                    constexpr int K = decltype(kc)::value, Q0 = decltype(q0c)::value, Q1 = decltype(q1c)::value;
+                    constexpr bool REV = decltype(revc)::value != 0;
                     float w0[CPL], w1[CPL];
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
+                    for (int i = Q0; i < Q1; ++i) {
+                        const int q = REV ? Q1 - 1 - (i - Q0) : i;
                         w1[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awj[q]);
                         w0[q] = lds_f32<K * 2 * Cfg::XYP * 4>(awi[q]);
                     }
@@ -1103,7 +1146,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
 #pragma unroll
                     for (int kp = 0; kp < ZP; ++kp) zsum[kp] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
+                    for (int i = Q0; i < Q1; ++i) {
+                        const int q = REV ? Q1 - 1 - (i - Q0) : i;
                         const float w = w1[q] * w0[q];  // psi(Y) * psi(X)
                         const float2 ww = make_float2(w, w);
 #pragma unroll
@@ -1113,6 +1157,15 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
 #pragma unroll
                     for (int kp = 0; kp < ZP; ++kp) sum = ffma2(wz[kp], zsum[kp], sum);
                     return sum.x + sum.y;
+                };
+                auto gpoint = [&](auto kc) {
+                    constexpr int K = decltype(kc)::value;
+                    if constexpr (Cfg::ROWSKIP) {
+                        if (skipmask & (1u << (3 * K + 1))) return gbody(kc, IntC<1>{}, IntC<CPL>{}, IntC<1>{});
+                        return gbody(kc, IntC<0>{}, IntC<CPL - 1>{}, IntC<0>{});
+                    } else {
+                        return gbody(kc, IntC<0>{}, IntC<CPL>{}, IntC<0>{});
+                    }
                 };
 #define NFFT_GSLOT(K)                                                                      \
                 case K:                                                                    \
