@@ -195,6 +195,12 @@ struct RegCfg {
 #ifndef NFFT_REG_ROWSKIP
 #define NFFT_REG_ROWSKIP 1
 #endif
+// Measured on the B200 at c4 (profiles/r02i_ab.txt): gather 3.23 -> 3.05 ms, but the SPREAD gets slower with the two
+// variants (4.02 -> 4.94 ms; no spills, fewer instructions per point -- the accumulators live across points there and
+// the second body order costs more than the six FFMA2s save), so only the gather uses them.
+#ifndef NFFT_REG_ROWSKIP_SPREAD
+#define NFFT_REG_ROWSKIP_SPREAD 0
+#endif
     static constexpr bool ROWSKIP = NFFT_REG_ROWSKIP && CPL > 2 && ROW_FIRST_MAX + 1 == ROW_LAST_MIN - LC + 1 &&
                                     ROW_FIRST_MAX + 1 == SY - 1;  // oy <= ROW_FIRST_MAX <=> last group empty; else first
     static constexpr int WIN_FLOATS = (2 * kRegGroup * XYP + 3) / 4 * 4 + kRegGroup * ZWP;
@@ -859,6 +865,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
 #else
                 const unsigned skipmask = stage_windows<Cfg, LC, true>(g, pts_sh, base, npts, wbase, lane, pow2);
 #endif
+                (void)skipmask;
                 // One copy of the point body per slot of the round (window loads with immediate offsets),
                 // entered through a switch; a slot that ends a supercell leaves the switch so that the ONE
                 // copy of the add-out code above it runs, and the switch is re-entered at the next slot.
@@ -896,7 +903,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                     };
                     auto point = [&](auto kc) {
                         constexpr int K = decltype(kc)::value;
-                        if constexpr (Cfg::ROWSKIP) {
+                        if constexpr (Cfg::ROWSKIP && NFFT_REG_ROWSKIP_SPREAD) {
                             // warp-uniform (a ballot): set = the first group of this point is all zero, else the last
                             if (skipmask & (1u << (3 * K + 1)))
                                 body(kc, IntC<1>{}, IntC<CPL>{}, IntC<1>{});
