@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU session 8: final evidence of the consolidated build: tests, smoke, bench (both arms), ncu launch list + capture.
-R=${1:-r02h}
+R=${1:-r02j}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_pytest_gpu.log 2>&1; PRC=$?; echo "pytest rc=$PRC"; tail -4 gpurun_out/${R}_pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
