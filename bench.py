@@ -219,6 +219,56 @@ def bind_to_gpu_numa_node(torch, local):
     return None
 
 
+def pick_host_numa_node(torch, dev):
+    """When sysfs does not say which NUMA node the GPU hangs off (VMs), measure it: pin this process to each node
+    in turn, allocate a pinned buffer there (first touch) and time host->device copies; stay on the fastest node
+    for the pinned staging buffers of the end-to-end arm.  Returns (node or None, {node: GB/s})."""
+    try:
+        nodes = sorted(int(n[4:]) for n in os.listdir("/sys/devices/system/node") if n.startswith("node") and n[4:].isdigit())
+    except OSError:
+        return None, {}
+    allowed0 = os.sched_getaffinity(0)
+    cpus = {}
+    for node in nodes:
+        try:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                ids = set()
+                for part in f.read().strip().split(","):
+                    if part:
+                        lo, _, hi = part.partition("-")
+                        ids.update(range(int(lo), int(hi or lo) + 1))
+            if ids & allowed0:
+                cpus[node] = ids & allowed0
+        except (OSError, ValueError):
+            pass
+    if len(cpus) < 2:
+        return None, {}
+    dst = torch.empty(32 << 20, dtype=torch.uint8, device=dev)
+    rates = {}
+    for node, ids in cpus.items():
+        try:
+            os.sched_setaffinity(0, ids)
+            src = torch.empty(32 << 20, dtype=torch.uint8).fill_(1).pin_memory()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            rates[node] = 4 * src.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            del src
+        except Exception:
+            pass
+    if not rates:
+        os.sched_setaffinity(0, allowed0)
+        return None, {}
+    best = max(rates, key=rates.get)
+    os.sched_setaffinity(0, cpus[best])
+    return best, {str(k): round(v, 1) for k, v in rates.items()}
+
+
 def time_pairs(torch, T, workload, dev, steps, warmup=3, seed=99, graph=False):
     """Device-timed adjoint+forward pairs of another BASELINE workload (inputs resident, one binning per step):
     the `extra_workloads` entries of the default line."""
@@ -371,6 +421,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(torch, local)   # before any pinned allocation: first touch decides the node
+    numa_rates = {}
+    if numa is None and not args.no_extras:
+        numa, numa_rates = pick_host_numa_node(torch, dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     d, N, m, n, B, C, distribution = WORKLOADS[args.workload]
@@ -568,7 +621,7 @@ def run_ours(args):
             "e2e": {"value": n * world / (ms_e2e / args.steps * 1e-3), "unit": "points/s",
                     "h2d_bytes_per_step": n * (4 * d + 4 * C) + 8 * (B + 1),
                     "d2h_bytes_per_step": B * C * N ** d * 8 + n * C * 4,
-                    "host_numa_node_rank0": numa},
+                    "host_numa_node_rank0": numa, "h2d_gbs_by_numa_node_rank0": numa_rates},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "spread kernel (adjoint window convolution; spread_reg_kernel at c4)",
