@@ -265,7 +265,7 @@ def pick_host_numa_node(torch, dev):
         os.sched_setaffinity(0, allowed0)
         return None, {}
     best = max(rates, key=rates.get)
-    os.sched_setaffinity(0, cpus[best])
+    os.sched_setaffinity(0, cpus[best])   # the caller restores the full mask once its pinned buffers exist
     return best, {str(k): round(v, 1) for k, v in rates.items()}
 
 
@@ -422,6 +422,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(torch, local)   # before any pinned allocation: first touch decides the node
     numa_rates = {}
+    cpus_before = os.sched_getaffinity(0)
     if numa is None and not args.no_extras:
         numa, numa_rates = pick_host_numa_node(torch, dev)
     if world > 1:
@@ -435,6 +436,8 @@ def run_ours(args):
     h_pos, h_x, h_ptr = (t.cpu().pin_memory() for t in (pos, x, ptr))
     h_spec = torch.empty((B,) + (N,) * d + (C,), dtype=torch.complex64).pin_memory()
     h_y = torch.empty((n, C), dtype=torch.float32).pin_memory()
+    if numa_rates:
+        os.sched_setaffinity(0, cpus_before)   # the staging buffers are placed: give the CPU baseline all cores back
 
     def pair(x_, pos_, ptr_):
         # every step is a fresh transform pair: its points are binned once (NfftPlan) and the adjoint and the
