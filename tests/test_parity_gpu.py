@@ -404,7 +404,7 @@ def test_plan_reuses_the_binning_between_transforms():
     assert plan.sorts == 1 and 4 * pos.shape[0] <= plan.nbytes < 8 * pos.shape[0] + (1 << 20)
     assert O.rel_l2(y0.cpu().numpy(), ref_y) < TOL and O.rel_l2(y.cpu().numpy(), ref_y) < TOL
     assert O.rel_l2(y2.cpu().numpy(), ref_y) < TOL and O.rel_l2(f.cpu().numpy(), ref_f) < TOL
-    assert plan.dropped_points() == 0
+    assert plan.flags() == {"dropped": 0, "tma_timeouts": 0}
     # a plan refuses other tensors
     with pytest.raises(RuntimeError):
         T.nfft_adjoint(tx, cuda(pos), tb, 32, 4, plan=plan)

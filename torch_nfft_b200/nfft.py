@@ -182,19 +182,25 @@ class NfftPlan:
         """Number of distinct tilings the points have been binned for."""
         return len(self._sorts)
 
-    def dropped_points(self):
-        """Points that transforms using this plan found outside their tile, i.e. evidence that the positions
-        changed after the plan was made.  Reads a device counter: synchronises the current stream."""
+    def flags(self):
+        """Device-side counters of the binnings made so far, summed: `dropped` = points that transforms using this
+        plan found outside their tile (evidence that the positions changed after the plan was made), `tma_timeouts`
+        = TMA tile loads that did not complete (must be 0).  Reads device memory: synchronises the current stream."""
         import ctypes
         L = _lib.lib()
-        total = 0
+        dropped = timeouts = 0
         out = (ctypes.c_uint32 * 8)()
         with torch.cuda.device(self.device):
             for buf, args in self._sorts.values():
                 _lib.check(L.nfftb200_plan_flags(buf.data_ptr(), *args, ctypes.cast(out, ctypes.c_void_p),
                                                  _stream_ptr(self.device)), "plan_flags")
-                total += int(out[0])
-        return total
+                dropped += int(out[0])
+                timeouts += int(out[1])
+        return {"dropped": dropped, "tma_timeouts": timeouts}
+
+    def dropped_points(self):
+        """Points that transforms using this plan found outside their tile (see `flags`).  Synchronises."""
+        return self.flags()["dropped"]
 
 
 def _resolve_points(pos, batch, batch_size, batch_ptr, plan):
