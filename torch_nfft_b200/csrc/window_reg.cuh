@@ -512,15 +512,19 @@ static_assert(kRegMaxPts % 16 == 0, "the tap windows behind the u8 offsets must 
 // s_expect (spread with the TMA flush, else nullptr): s_expect[p] = number of units that will add into plane
 // pair p of the tile -- a unit whose first / last point lies in supercell s0 / s1 of its column adds into the
 // pairs s0 * sp .. min(s1 * sp + zp, npairs) - 1, each exactly once (see advance() in the spread kernel).
+// units: how many units a batch is cut into when its columns are uneven (NFFT_REG_UNITS = 2 per warp for the
+// 4 x 4 x 2 sweep; one per warp for the dense 2 x 2 x 2 sweep, where every unit ends with an add-out of all its
+// plane pairs under the same few locks: c5 24.5 -> 23.0 ms, profiles/r02l_c5.txt)
 __device__ __forceinline__ void make_units(const int* s_start, int ncols, int nsz, int* s_units, int* s_nunits,
-                                           int* s_expect = nullptr, int sp = 0, int zp = 0, int npairs = 0) {
+                                           int* s_expect = nullptr, int sp = 0, int zp = 0, int npairs = 0,
+                                           int units = NFFT_REG_UNITS) {
     __shared__ int s_raw[kRegMaxUnits], s_rawcnt[kRegMaxUnits];
     const int total = s_start[ncols * nsz] - s_start[0];
     const int maxseg = NFFT_REG_SPLIT && ncols <= 64 ? 16 : 1;  // sum of segments <= NFFT_REG_UNITS + ncols <= 80
     if ((int)threadIdx.x < ncols) {
         const int c0 = threadIdx.x * nsz;
         const int lo = s_start[c0], cnt = s_start[c0 + nsz] - lo;
-        int nseg = (int)(((long long)cnt * NFFT_REG_UNITS + total / 2) / (total > 0 ? total : 1));  // round(cnt / share)
+        int nseg = (int)(((long long)cnt * units + total / 2) / (total > 0 ? total : 1));  // round(cnt / share)
         nseg = nseg < 1 ? 1 : (nseg > maxseg ? maxseg : nseg);
         if (cnt < 2 * kRegGroup * nseg) nseg = cnt / (2 * kRegGroup) > 0 ? cnt / (2 * kRegGroup) : 1;  // >= 2 rounds each
         for (int j = 0; j < nseg && cnt > 0; ++j) {
@@ -730,7 +734,8 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     const int cnt = (int)(t.p_hi - t.p_lo);
     bucket_points<SX, SY, SZ, true>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
-    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, tma_tile ? s_expect : nullptr, SP, ZP, npairs);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, tma_tile ? s_expect : nullptr, SP, ZP, npairs,
+               SX == 2 ? kRegWarps : NFFT_REG_UNITS);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(0, 5, ph0, pha);
     NFFT_PHASE_ADD(0, 6, pha, phb);
@@ -1034,7 +1039,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     } else {
         cp_async_wait_all();  // make_units' barriers publish the tile to the other threads
     }
-    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits);
+    make_units(s_start, nsx * nsy, nsz, s_order, &s_nunits, nullptr, 0, 0, 0, SX == 2 ? kRegWarps : NFFT_REG_UNITS);
     NFFT_PHASE_MARK(ph1);
     NFFT_PHASE_ADD(1, 5, ph0, pha);
     NFFT_PHASE_ADD(1, 6, pha, phb);
