@@ -491,7 +491,9 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
             default: NF_FAIL(NFFTB200_ERR_INVALID, "register-stencil kernels need m <= 4");
         }
         const int nsc = ((g.T[0] + g.sc[0] - 1) / g.sc[0]) * ((g.T[1] + g.sc[1] - 1) / g.sc[1]) * ((g.T[2] + g.sc[2] - 1) / g.sc[2]);
-        const size_t smem = reg_smem_bytes(g, nsc, win_floats);
+        // experiment switch: NFFTB200_SMEM_PAD=<bytes> requests more shared memory per CTA (fewer resident CTAs)
+        static const size_t smem_pad = getenv("NFFTB200_SMEM_PAD") ? (size_t)atoll(getenv("NFFTB200_SMEM_PAD")) : 0;
+        const size_t smem = reg_smem_bytes(g, nsc, win_floats) + smem_pad;
         NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
         CUtensorMap tmap;
         a.use_tma = make_grid_tensor_map(g, a.grid, &tmap) ? 1 : 0;
