@@ -88,6 +88,7 @@ struct Geom {
     int sc[3];           // supercell extent per slot (3D register-stencil kernels: 4 x 4 x 2, dense point sets 2 x 2 x 2)
     int fine_xy_levels, fine_z_bits;  // log2 of the supercells per tile edge in X / Y, and in Z
     float inv_b, inv_sqrt_b_pi, c_hat;
+    float kexp[kMaxCutoff + 2];  // exp(-j^2 inv_b), j = 0 .. m + 1 (tap recurrence of the register-stencil kernels)
 };
 
 struct SortPlan {

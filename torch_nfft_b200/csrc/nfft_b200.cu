@@ -196,6 +196,7 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     // window parameters, evaluated like the reference's host macros
     g.inv_b = kThreeQuarterPi / (float)m;                 // WINDOW_FORWARD_PARAM1
     g.inv_sqrt_b_pi = sqrtf(0.75f / (float)m);            // WINDOW_FORWARD_PARAM2
+    for (int j = 0; j < kMaxCutoff + 2; ++j) g.kexp[j] = (float)exp(-(double)(j * j) * (double)g.inv_b);
     g.c_hat = kPiThird * (float)m / (float)(N * N);       // WINDOW_ADJOINT_PARAM
 
     // components per pass and tile extents

@@ -230,6 +230,37 @@ __device__ __forceinline__ float window_exp(float x) {
 #endif
 }
 
+// Tap recurrence (pow2 grids): the L taps phi(frac + j), j = m .. -(m + 1), of one point and dimension are
+//   amp exp(-(frac + j)^2 inv_b) = [amp exp(-frac^2 inv_b)] * exp(-2 frac inv_b)^j * exp(-j^2 inv_b)
+// = e0 * u^j * k_j: THREE exponentials (e0, u, 1/u) and ~2.5 multiplications per tap instead of one exponential
+// and six other instructions per tap (k_j = Geom::kexp, constant-bank operands).  The powers are built by
+// multiplication, so the rounding of u enters a tap |j| times: <= ~20 ulp on the outermost taps (values <= 1e-6
+// of the centre), ~4 ulp on the central ones -- measured against the oracle in profiles/r02p_ab.txt.
+#ifndef NFFT_WINDOW_RECUR
+#define NFFT_WINDOW_RECUR 0
+#endif
+template <int LC, typename Store>
+__device__ __forceinline__ void window_taps_recur(const Geom& g, float frac, float amp, Store store) {
+    constexpr int m = (LC - 2) / 2;
+    const float a = frac * g.inv_b;
+    const float e0 = window_exp(-frac * a) * amp;
+    float up[m + 2], vp[m + 2], ek[m + 2];
+    up[1] = window_exp(-2.f * a);
+    vp[1] = window_exp(2.f * a);
+#pragma unroll
+    for (int j = 2; j <= m + 1; ++j) {
+        up[j] = up[j / 2] * up[j - j / 2];
+        vp[j] = vp[j / 2] * vp[j - j / 2];
+    }
+#pragma unroll
+    for (int j = 0; j <= m + 1; ++j) ek[j] = e0 * g.kexp[j];
+#pragma unroll
+    for (int l = 0; l < LC; ++l) {
+        const int j = m - l;  // tap l sits at frac + (m - l)
+        store(l, j == 0 ? ek[0] : (j > 0 ? ek[j] * up[j] : ek[-j] * vp[-j]));
+    }
+}
+
 // Shared-memory spin lock of the add-out (lane 0 of the warp).  Experiment switches for the next A/B run
 // (the r01e capture counts 11 CAS attempts per acquisition): NFFT_REG_LOCK_TTAS=1 polls the lock word
 // with a plain volatile load and tries the CAS only when it reads free; NFFT_REG_LOCK_NS is the back-off.
@@ -608,11 +639,15 @@ __device__ __forceinline__ unsigned stage_windows(const Geom& g, uint32_t pts_sh
             // frac = pm - fl is exact; frac + (m - l) is ONE rounding of the exact value, i.e. bit-identical
             // to the reference's (float)((double)pos * 2N - shift - l)
             const float frac = pm - fl;
+#if NFFT_WINDOW_RECUR
+            window_taps_recur<LC>(g, frac, amp, [&](int l, float v) { sts_at(dst + 4u * l, v); });
+#else
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
                 sts_at(dst + 4u * l, window_exp(-(tt * tt) * g.inv_b) * amp);  // eval_phi, :24-28
             }
+#endif
         } else {
             const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
 #pragma unroll
@@ -661,11 +696,15 @@ __device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const f
             // frac = pm - fl is exact; frac + (m - l) is ONE rounding of the exact value, i.e. bit-identical
             // to the reference's (float)((double)pos * 2N - shift - l)
             const float frac = pm - fl;
+#if NFFT_WINDOW_RECUR
+            window_taps_recur<LC>(g, frac, amp, [&](int l, float v) { dst[l] = v; });
+#else
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
                 dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;  // eval_phi, :24-28
             }
+#endif
         } else {
             const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
 #pragma unroll

@@ -134,11 +134,15 @@ __device__ __forceinline__ void stage_windows_2d(const Geom& g, const float* s_r
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
         if (pow2) {
             const float frac = pm - fl;  // exact; one rounding per tap below, see window_reg.cuh
+#if NFFT_WINDOW_RECUR
+            window_taps_recur<LC>(g, frac, g.inv_sqrt_b_pi, [&](int l, float v) { dst[l] = v; });
+#else
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
                 dst[l] = window_exp(-(tt * tt) * g.inv_b) * g.inv_sqrt_b_pi;  // eval_phi, :24-28
             }
+#endif
         } else {
             const double bd = (double)p * (double)g.M - (double)((int)fl - g.m);
 #pragma unroll
