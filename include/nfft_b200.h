@@ -170,9 +170,9 @@ int nfftb200_sort_points(const float* pos, const int64_t* batch, uint32_t* keys_
                          int m, int64_t B, int64_t C, int flags, void* workspace,
                          size_t workspace_bytes, void* stream);
 
-/* Host-only: the tiling the engine would use.  out[25] = dim,N,M,m,L, T[3], nt[3], P[3], sY, sZ,
+/* Host-only: the tiling the engine would use.  out[28] = dim,N,M,m,L, T[3], nt[3], P[3], sY, sZ,
  * tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits, supercell[3] (slot order X,Y,Z; see
- * DESIGN.md). */
+ * DESIGN.md), mixed (density decided per tile on the device), refine_pass, dense_tile_pts. */
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n,
                             int32_t* out);
 
@@ -184,6 +184,11 @@ int nfftb200_profile_read(double* ms_out, int64_t* count_out);
 
 /* Tests: force the 64-bit index variants of the spectral kernels (normally chosen when B*C*M^d >= 2^31). */
 void nfftb200_debug_force_int64(int on);
+
+/* Tests / experiments: mixed-density mode of the 3D register-stencil path (heavy tiles swept with 2 x 2 x 2
+ * supercells, decided on the device).  mode -1 = default, 0 = off, 1 = on; min_points = smallest point set
+ * that uses it (-1 = default 2^20); dense_tile_pts = points that make a 16^3 tile heavy (<= 0 = default 8192). */
+void nfftb200_debug_mixed(int mode, int64_t min_points, int dense_tile_pts);
 
 /* cuFFT plan cache: an LRU of handles per (device, dimension, M, type, B*C).  _clear destroys them (all
  * devices) and fails with NFFTB200_ERR_INVALID while the cache is pinned; _pin(+1/-1) is called by owners of

@@ -439,7 +439,10 @@ def sort_keys(pos, batch, N, tile, fine_bits=0, supercell=(2, 4, 4)):
     for b in range(levels - 1, -1, -1):
         fine = (fine << 2) | (((by >> b) & 1) << 1) | ((bx >> b) & 1)
     fine = (fine << zbits) | bz
-    return ((key << fine_bits) | (fine >> (2 * levels + zbits - fine_bits))).astype(np.int64)
+    total = 2 * levels + zbits
+    if fine_bits >= total:  # mixed-density keys: the index left-aligned in a wider field
+        return ((key << fine_bits) | (fine << (fine_bits - total))).astype(np.int64)
+    return ((key << fine_bits) | (fine >> (total - fine_bits))).astype(np.int64)
 
 
 def stable_permutation(keys):

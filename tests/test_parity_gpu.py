@@ -404,7 +404,7 @@ def test_plan_reuses_the_binning_between_transforms():
     assert plan.sorts == 1 and 4 * pos.shape[0] <= plan.nbytes < 8 * pos.shape[0] + (1 << 20)
     assert O.rel_l2(y0.cpu().numpy(), ref_y) < TOL and O.rel_l2(y.cpu().numpy(), ref_y) < TOL
     assert O.rel_l2(y2.cpu().numpy(), ref_y) < TOL and O.rel_l2(f.cpu().numpy(), ref_f) < TOL
-    assert plan.flags() == {"dropped": 0, "tma_timeouts": 0}
+    assert plan.flags() == {"dropped": 0, "tma_timeouts": 0, "clustered": 0}
     # a plan refuses other tensors
     with pytest.raises(RuntimeError):
         T.nfft_adjoint(tx, cuda(pos), tb, 32, 4, plan=plan)
@@ -568,3 +568,88 @@ def test_cuda_graph_capture_and_replay(d, N, m, B, n):
         T.clear_caches()
     graphed.close()
     T.clear_caches()
+
+
+# ---------------------------------------------------------------------------------------------
+# mixed density (large 3D point sets): whether the set is clustered is decided on the device from a sample of
+# the keys; heavy tiles are then swept with 2 x 2 x 2 supercells, the rest with 4 x 4 x 2
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture
+def mixed_mode():
+    L = _lib.lib()
+    L.nfftb200_debug_mixed(1, 0, 600)  # on for every size; a 16^3 tile is heavy from 600 points
+    yield
+    L.nfftb200_debug_mixed(-1, -1, 0)
+
+
+def clustered_points(rng, n, B, sigma=0.03, uniform_share=0.2):
+    """B point sets: three Gaussian clusters each plus a uniform background, wrapped into [-1/2, 1/2)."""
+    nu = int(n * uniform_share)
+    per = (n - nu) // 3
+    sets = []
+    for _ in range(B):
+        centres = rng.random((3, 3)) - 0.5
+        pts = [centres[k] + sigma * rng.standard_normal((per, 3)) for k in range(3)]
+        pts.append(rng.random((n - 3 * per, 3)) - 0.5)
+        p = np.concatenate(pts)
+        sets.append(((p + 0.5) % 1.0 - 0.5).astype(np.float32))
+    pos = np.concatenate(sets)
+    pos[pos >= 0.5] = -0.5
+    batch = np.repeat(np.arange(B, dtype=np.int64), n)
+    return pos, batch
+
+
+@pytest.mark.parametrize("m,cplx", [(4, False), (3, True)])
+def test_mixed_density_transforms(mixed_mode, m, cplx):
+    rng = np.random.default_rng(40 + m)
+    N, B, n = 32, 2, 15000
+    geo = _lib.geometry(3, N, m, B, 1, 0, B * n)
+    assert geo["mixed"] == 1 and geo["refine_pass"] == 1 and geo["dense_tile_pts"] == 600
+    for clustered in (True, False):
+        if clustered:
+            pos, batch = clustered_points(rng, n, B)
+        else:
+            pos, batch = make_points(rng, 3, B, n)
+        x = make_values(rng, (pos.shape[0],), cplx)
+        tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
+        plan = T.NfftPlan(tp, tb)
+        y = T.nfft_adjoint(tx, plan=plan, N=N, m=m)
+        ref_y = O.nfft_adjoint(x, pos, batch, N, m)
+        assert O.rel_l2(y.cpu().numpy(), ref_y) < TOL
+        f = T.nfft_forward(y, plan=plan, m=m)
+        assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, m)) < TOL
+        # the device-side decision: heavy tiles exist only in the clustered set
+        assert plan.flags() == {"dropped": 0, "tma_timeouts": 0, "clustered": 1 if clustered else 0}
+        # the same transforms without a kept plan, and against the single-sweep path
+        y1 = T.nfft_adjoint(tx, tp, tb, N, m)
+        _lib.lib().nfftb200_debug_mixed(0, 0, 0)
+        y0 = T.nfft_adjoint(tx, tp, tb, N, m)
+        _lib.lib().nfftb200_debug_mixed(1, 0, 600)
+        assert O.rel_l2(y1.cpu().numpy(), ref_y) < TOL and O.rel_l2(y0.cpu().numpy(), y1.cpu().numpy()) < 2e-6
+
+
+def test_mixed_density_binning_is_bit_exact(mixed_mode):
+    """The conditional low radix pass: a clustered set is sorted by the full key, a uniform one by the key
+    without its low digit (tile + the top fine bits), both stable."""
+    rng = np.random.default_rng(77)
+    N, m, B, n = 32, 4, 2, 20000
+    L = _lib.lib()
+    for clustered in (True, False):
+        pos, batch = clustered_points(rng, n, B) if clustered else make_points(rng, 3, B, n)
+        nn = pos.shape[0]
+        keys = torch.zeros(nn, dtype=torch.int32, device=DEV)
+        perm = torch.zeros(nn, dtype=torch.int32, device=DEV)
+        tile = (ctypes.c_int32 * 3)()
+        nb = L.nfftb200_workspace_bytes(_lib.OP_SORT, nn, 0, 3, N, m, B, 1, 0)
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        tp, tb = cuda(pos), cuda(batch)
+        _lib.check(L.nfftb200_sort_points(tp.data_ptr(), tb.data_ptr(), keys.data_ptr(), perm.data_ptr(),
+                                          ctypes.cast(tile, ctypes.c_void_p), nn, 3, N, m, B, 1, 0, ws.data_ptr(),
+                                          ws.numel(), torch.cuda.current_stream().cuda_stream), "sort")
+        torch.cuda.synchronize()
+        geo = _lib.geometry(3, N, m, B, 1, 0, nn)
+        assert geo["mixed"] == 1 and geo["fine_bits"] == 9 and (geo["scx"], geo["scy"], geo["scz"]) == (2, 2, 2)
+        okeys = O.sort_keys(pos, batch, N, list(tile)[::-1], geo["fine_bits"], (2, 2, 2))
+        assert np.array_equal(keys.cpu().numpy().astype(np.int64), okeys)
+        expect = O.stable_permutation(okeys if clustered else okeys >> 8)
+        assert np.array_equal(perm.cpu().numpy().astype(np.int64), expect)

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "nfftb200_plan_cache_pin": (ctypes.c_int, [_i32]),
     "nfftb200_plan_cache_size": (ctypes.c_int, []),
     "nfftb200_debug_force_int64": (None, [_i32]),
+    "nfftb200_debug_mixed": (None, [_i32, _i64, _i32]),
     # (n, n_geom, d, N, m, B, C, flags)
     "nfftb200_plan_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32]),
     # (pos, batch, plan, plan_bytes, n, n_geom, d, N, m, B, C, flags, ws, ws_bytes, stream)
@@ -98,12 +99,13 @@ def launch_count() -> int:
 
 
 GEOMETRY_FIELDS = ("dim", "N", "M", "m", "L", "Tx", "Ty", "Tz", "ntx", "nty", "ntz", "Px", "Py", "Pz", "sY", "sZ",
-                   "tile_elems", "ncomp", "pmax", "spread_threads", "use_reg", "fine_bits", "scx", "scy", "scz")
+                   "tile_elems", "ncomp", "pmax", "spread_threads", "use_reg", "fine_bits", "scx", "scy", "scz", "mixed",
+                   "refine_pass", "dense_tile_pts")
 
 
 def geometry(d, N, m, B=1, C=1, flags=0, n=0):
     """Tiling the engine uses for a transform (host-only query)."""
-    out = (ctypes.c_int32 * 25)()
+    out = (ctypes.c_int32 * 28)()
     check(lib().nfftb200_debug_geometry(d, N, m, B, C, flags, n, ctypes.cast(out, ctypes.c_void_p)), "geometry")
     return dict(zip(GEOMETRY_FIELDS, list(out)))
 

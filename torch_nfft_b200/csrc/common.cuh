@@ -87,6 +87,10 @@ struct Geom {
     int fine_bits;       // low bits of a sort key: position of the point's supercell inside its tile (sort.cuh)
     int sc[3];           // supercell extent per slot (3D register-stencil kernels: 4 x 4 x 2, dense point sets 2 x 2 x 2)
     int fine_xy_levels, fine_z_bits;  // log2 of the supercells per tile edge in X / Y, and in Z
+    int mixed;           // 1: density decided per TILE on the device (3D register-stencil kernels, sort.cuh: refine pass +
+                         //    work-item classes); sc[] then describes the 2 x 2 x 2 hierarchy of the fine key bits
+    int refine_pass;     // mixed: the lowest radix pass covers fine key bits only and is conditional (sort_points)
+    int dense_tile_pts;  // mixed: a tile with at least this many points is swept with 2 x 2 x 2 supercells
     float inv_b, inv_sqrt_b_pi, c_hat;
     float kexp[kMaxCutoff + 2];  // exp(-j^2 inv_b), j = 0 .. m + 1 (tap recurrence of the register-stencil kernels)
 };

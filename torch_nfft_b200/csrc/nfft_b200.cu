@@ -171,6 +171,14 @@ static int sm_count() {
     return v;
 }
 
+// Mixed-density mode of the 3D register-stencil path (make_geom): -1 = default (on unless NFFTB200_NO_MIXED /
+// NFFTB200_NO_DENSE), 0 = off, 1 = on; point sets below g_mixed_min_points never use it (two sweeps are launched
+// and the keys are sampled: not worth it for small sets).  Test hook: nfftb200_debug_mixed.
+static std::atomic<int> g_mixed_mode{-1};
+static std::atomic<long long> g_mixed_min_points{1ll << 20};
+static std::atomic<int> g_mixed_dense_pts{0};  // 0: kDenseTilePts / NFFTB200_DENSE_TILE_PTS
+constexpr int kDenseTilePts = 8192;  // 2 points per oversampled cell of a 16^3 tile
+
 static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, bool cplx, int64_t n_points) {
     if (d < 1 || d > 3) NF_FAIL(NFFTB200_ERR_INVALID, "dimension d=%d not in [1,3]", d);
     if (N < 2 || (N & 1)) NF_FAIL(NFFTB200_ERR_INVALID, "bandwidth N=%lld must be even and >= 2", (long long)N);
@@ -251,24 +259,49 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     // * Fine key bits (sort.cuh: fine_index): the bits that fit the radix passes the tile key needs anyway are
     //   free; a dense set gets at least 4 of them even if that adds a pass, because its tiles are cut into many
     //   chunks and compact chunks are what lets the points of a chunk share register blocks.
+    // * Mixed density (everything else that is large enough): whether a point set is CLUSTERED is not known on
+    //   the host, so it is decided on the device, per tile.  The keys carry the 2 x 2 x 2 hierarchy, laid out so
+    //   that the lowest radix pass covers fine bits only; that pass runs only when a sample of the keys finds a
+    //   clustered set (sort.cuh: sort_points), and the work items of heavy tiles (>= dense_tile_pts points) are
+    //   then marked for the 2 x 2 x 2 sweep: launch_window starts both sweeps, each takes its class of tiles.
     g.fine_bits = g.fine_xy_levels = g.fine_z_bits = 0;
     g.sc[0] = g.sc[1] = g.sc[2] = 1;
+    g.mixed = g.refine_pass = g.dense_tile_pts = 0;
     static const bool no_fine = getenv("NFFTB200_NO_FINE_SORT") != nullptr;
     static const bool no_dense = getenv("NFFTB200_NO_DENSE") != nullptr;
+    static const bool no_mixed = getenv("NFFTB200_NO_MIXED") != nullptr;
+    static const int env_dense_pts = getenv("NFFTB200_DENSE_TILE_PTS") ? atoi(getenv("NFFTB200_DENSE_TILE_PTS")) : 0;
     if (g.use_reg == 1) {
         const bool full_tiles = g.T[0] == 16 && g.T[1] == 16 && g.T[2] == 16;
         const bool dense = (double)n_points >= (double)B * (double)g.Md;
         g.sc[0] = kRegSX, g.sc[1] = kRegSY, g.sc[2] = kRegSZ;
-        if (dense && full_tiles && !no_dense && (m == 3 || m == 4)) g.sc[0] = g.sc[1] = g.sc[2] = 2;
+        const bool small_kernels = full_tiles && (m == 3 || m == 4);  // spread/gather_reg_kernel<L, 2, 2, 2> exist
+        if (dense && small_kernels && !no_dense) g.sc[0] = g.sc[1] = g.sc[2] = 2;
+        int tile_bits = 0;
+        while ((1ll << tile_bits) < (long long)g.tiles_per_batch * B) ++tile_bits;
+        const int spare = (tile_bits + 7) / 8 * 8 - tile_bits;
+        const int mixed_mode = g_mixed_mode.load();
+        const long long mixed_min = g_mixed_min_points.load();
+        if (g.sc[0] != 2 && small_kernels && !no_fine && tile_bits > 0 && n_points >= mixed_min &&
+            (mixed_mode == 1 || (mixed_mode < 0 && !no_mixed && !no_dense))) {
+            const int total = 9;  // 2 x 2 x 2 supercells in a 16^3 tile: 3 (y, x) levels + 3 z bits
+            const int fb = spare >= total ? total : spare + 8;
+            if (tile_bits + fb <= 31) {
+                g.mixed = 1;
+                g.refine_pass = spare < total;
+                const int hook_pts = g_mixed_dense_pts.load();
+                g.dense_tile_pts = hook_pts > 0 ? hook_pts : (env_dense_pts > 0 ? env_dense_pts : kDenseTilePts);
+                g.sc[0] = g.sc[1] = g.sc[2] = 2;  // (of the key hierarchy; the sweep is chosen per tile)
+                g.fine_xy_levels = g.fine_z_bits = 3;
+                g.fine_bits = fb;
+            }
+        }
         auto log2i = [](int v) { int b = 0; while ((1 << b) < v) ++b; return b; };
         const bool pow2_cells = g.sc[0] == g.sc[1] && (g.sc[0] & (g.sc[0] - 1)) == 0 && (g.sc[2] & (g.sc[2] - 1)) == 0;
-        if (full_tiles && pow2_cells && !no_fine) {
+        if (!g.mixed && full_tiles && pow2_cells && !no_fine) {
             g.fine_xy_levels = log2i(16 / g.sc[0]);
             g.fine_z_bits = log2i(16 / g.sc[2]);
             const int total = 2 * g.fine_xy_levels + g.fine_z_bits;
-            int tile_bits = 0;
-            while ((1ll << tile_bits) < (long long)g.tiles_per_batch * B) ++tile_bits;
-            const int spare = (tile_bits + 7) / 8 * 8 - tile_bits;
             int k = spare < total ? spare : total;
             // a dense set whose tile key leaves fewer than 4 spare bits pays one more radix pass for compact chunks
             // (c5: 9 tile bits, 7 spare: its 2^26-point sort costs 2.6 ms per pass, profiles/r02f_c5.txt)
@@ -462,9 +495,15 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
     if (g.use_reg == 1) {
         // supercell kRegSX x kRegSY x kRegSZ = 4 x 4 x 2 cells; for m = 4 the register block is 13 x 13 x 12:
         // 6 positions x 6 float2 accumulators per lane
+        // mixed density: both sweeps are launched, each takes the work items of its class of tiles
+        const int nsweeps = g.mixed ? 2 : 1;
+        for (int sweep = 0; sweep < nsweeps; ++sweep) {
         WindowKernelTma kern = nullptr;
         int win_floats = 0;
-        const bool small_cells = g.sc[0] == 2 && g.sc[1] == 2 && g.sc[2] == 2;  // dense point sets, m = 3, 4
+        // 2 x 2 x 2 supercells: dense point sets (m = 3, 4), or the heavy tiles of a mixed set
+        const bool small_cells = g.mixed ? sweep == 1 : (g.sc[0] == 2 && g.sc[1] == 2 && g.sc[2] == 2);
+        const int scx = small_cells ? 2 : kRegSX, scy = small_cells ? 2 : kRegSY, scz = small_cells ? 2 : kRegSZ;
+        a.item_sel = g.mixed ? 1 + sweep : 0;
         switch (g.m) {
 #define NF_REG_CASE(M_, L_)                                                                          \
             case M_:                                                                                 \
@@ -491,7 +530,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
 #undef NF_REG_CASE_DENSE
             default: NF_FAIL(NFFTB200_ERR_INVALID, "register-stencil kernels need m <= 4");
         }
-        const int nsc = ((g.T[0] + g.sc[0] - 1) / g.sc[0]) * ((g.T[1] + g.sc[1] - 1) / g.sc[1]) * ((g.T[2] + g.sc[2] - 1) / g.sc[2]);
+        const int nsc = ((g.T[0] + scx - 1) / scx) * ((g.T[1] + scy - 1) / scy) * ((g.T[2] + scz - 1) / scz);
         // experiment switch: NFFTB200_SMEM_PAD=<bytes> requests more shared memory per CTA (fewer resident CTAs)
         static const size_t smem_pad = getenv("NFFTB200_SMEM_PAD") ? (size_t)atoll(getenv("NFFTB200_SMEM_PAD")) : 0;
         const size_t smem = reg_smem_bytes(g, nsc, win_floats) + smem_pad;
@@ -501,6 +540,7 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         for (int k0 = 0; k0 < g.K; ++k0) {
             a.k0 = k0;
             NF_LAUNCH(kern, (unsigned)sp.max_items, kRegThreads, smem, st, g, a, tmap);
+        }
         }
         return NFFTB200_OK;
     }
@@ -862,14 +902,20 @@ int64_t nfftb200_launch_count(void) { return (int64_t)g_launches.load(); }
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n, int32_t* out) {
     Geom g;
     NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
-    int v[25] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
+    int v[28] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
                  g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg, g.fine_bits, g.sc[0], g.sc[1],
-                 g.sc[2]};
-    for (int i = 0; i < 25; ++i) out[i] = v[i];
+                 g.sc[2], g.mixed, g.refine_pass, g.dense_tile_pts};
+    for (int i = 0; i < 28; ++i) out[i] = v[i];
     return NFFTB200_OK;
 }
 
 void nfftb200_debug_force_int64(int on) { g_force_int64.store(on ? 1 : 0); }
+
+void nfftb200_debug_mixed(int mode, int64_t min_points, int dense_tile_pts) {
+    g_mixed_mode.store(mode < 0 ? -1 : (mode ? 1 : 0));
+    g_mixed_min_points.store(min_points < 0 ? (1ll << 20) : (long long)min_points);
+    g_mixed_dense_pts.store(dense_tile_pts > 0 ? dense_tile_pts : 0);
+}
 
 #ifdef NFFT_PHASE_TIMING
 // debug build only: out[2][24] = accumulated clock64() phase lengths of the register-stencil kernels

@@ -13,7 +13,8 @@
 
 namespace nfftb200 {
 
-constexpr int kPlanFlagWords = 8;  // plan flags: [0] points dropped by a window kernel (stale plan), [1] TMA timeouts
+constexpr int kPlanFlagWords = 8;  // plan flags: [0] points dropped by a window kernel (stale plan), [1] TMA timeouts,
+                                   // [2] Geom::mixed: the point set was found clustered and its keys were refined
 
 // ------------------------------------------------------------------------- block scan helpers
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
@@ -52,8 +53,10 @@ constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_reduce_kernel(const uint32_t* __restrict__ in, long long count, uint32_t* __restrict__ partial) {
+scan_reduce_kernel(const uint32_t* __restrict__ in, long long count, uint32_t* __restrict__ partial,
+                   const uint32_t* __restrict__ run_if = nullptr) {
     __shared__ uint32_t s_warp[33];
+    if (run_if && *run_if == 0) return;  // (uniform over the grid: a skipped conditional radix pass)
     const long long base = (long long)blockIdx.x * kScanTile;
     uint32_t s = 0;
     for (int k = 0; k < kScanItems; ++k) {
@@ -66,8 +69,10 @@ scan_reduce_kernel(const uint32_t* __restrict__ in, long long count, uint32_t* _
 }
 
 // single block: in-place exclusive scan of partial[0..nparts), total written to partial[nparts]
-__global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* partial, int nparts) {
+__global__ void __launch_bounds__(1024)
+scan_partials_kernel(uint32_t* partial, int nparts, const uint32_t* __restrict__ run_if = nullptr) {
     __shared__ uint32_t s_warp[33];
+    if (run_if && *run_if == 0) return;
     uint32_t running = 0;
     for (int base = 0; base < nparts; base += 1024) {
         int i = base + threadIdx.x;
@@ -83,8 +88,9 @@ __global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* partial, 
 // out[i] = exclusive prefix of in; out[count] = total.  in may alias out.
 __global__ void __launch_bounds__(kScanThreads)
 scan_final_kernel(const uint32_t* in, uint32_t* out, long long count, const uint32_t* __restrict__ partial,
-                  int nparts) {
+                  int nparts, const uint32_t* __restrict__ run_if = nullptr) {
     __shared__ uint32_t s_warp[33];
+    if (run_if && *run_if == 0) return;
     const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
     uint32_t s = 0;
@@ -109,8 +115,9 @@ scan_final_kernel(const uint32_t* in, uint32_t* out, long long count, const uint
 // instead of three.  Every thread owns a contiguous run of `per` items; in may alias out.
 constexpr long long kScanSmallMax = 1024 * 8;  // (a 64K-entry digit table through one block costs 85 us)
 __global__ void __launch_bounds__(1024)
-scan_small_kernel(const uint32_t* in, uint32_t* out, int count, int per) {
+scan_small_kernel(const uint32_t* in, uint32_t* out, int count, int per, const uint32_t* __restrict__ run_if = nullptr) {
     __shared__ uint32_t s_warp[33];
+    if (run_if && *run_if == 0) return;
     const int lo = threadIdx.x * per;
     const int hi = lo + per < count ? lo + per : count;
     uint32_t s = 0;
@@ -132,18 +139,19 @@ inline size_t scan_scratch_bytes(long long count) {
 }
 
 // exclusive scan of `count` uint32 (count >= 0); writes count+1 entries to out.
+// run_if (device, optional): the scan is skipped when *run_if == 0.
 inline int scan_exclusive(const uint32_t* in, uint32_t* out, long long count, uint32_t* scratch,
-                          cudaStream_t st) {
+                          cudaStream_t st, const uint32_t* run_if = nullptr) {
     if (count <= kScanSmallMax) {
         const int per = (int)((count + 1023) / 1024);
-        NF_LAUNCH(scan_small_kernel, 1, 1024, 0, st, in, out, (int)count, per < 1 ? 1 : per);
+        NF_LAUNCH(scan_small_kernel, 1, 1024, 0, st, in, out, (int)count, per < 1 ? 1 : per, run_if);
         return NFFTB200_OK;
     }
     int nparts = (int)((count + kScanTile - 1) / kScanTile);
     if (nparts < 1) nparts = 1;
-    NF_LAUNCH(scan_reduce_kernel, nparts, kScanThreads, 0, st, in, count, scratch);
-    NF_LAUNCH(scan_partials_kernel, 1, 1024, 0, st, scratch, nparts);
-    NF_LAUNCH(scan_final_kernel, nparts, kScanThreads, 0, st, in, out, count, scratch, nparts);
+    NF_LAUNCH(scan_reduce_kernel, nparts, kScanThreads, 0, st, in, count, scratch, run_if);
+    NF_LAUNCH(scan_partials_kernel, 1, 1024, 0, st, scratch, nparts, run_if);
+    NF_LAUNCH(scan_final_kernel, nparts, kScanThreads, 0, st, in, out, count, scratch, nparts, run_if);
     return NFFTB200_OK;
 }
 
@@ -220,9 +228,12 @@ __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, con
             key = key * (uint32_t)g.nt[slot] + (uint32_t)tile;
         }
     }
-    if (g.fine_bits > 0)
-        key = (key << g.fine_bits) |
-              (fine_index(in_tile[0], in_tile[1], in_tile[2], g) >> (2 * g.fine_xy_levels + g.fine_z_bits - g.fine_bits));
+    if (g.fine_bits > 0) {
+        // the top fine_bits bits of the hierarchical index (Geom::mixed: left-aligned in a field that may be wider)
+        const int total = 2 * g.fine_xy_levels + g.fine_z_bits;
+        const uint32_t fi = fine_index(in_tile[0], in_tile[1], in_tile[2], g);
+        key = (key << g.fine_bits) | (g.fine_bits >= total ? fi << (g.fine_bits - total) : fi >> (total - g.fine_bits));
+    }
     return key;
 }
 
@@ -270,8 +281,9 @@ constexpr int kRsBins = 256;
 // table[digit * nblocks + block] = number of keys of `block` whose digit is `digit`
 __global__ void __launch_bounds__(kRsThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ table,
-                  int nblocks) {
+                  int nblocks, const uint32_t* __restrict__ keys_alt = nullptr, const uint32_t* __restrict__ cond = nullptr) {
     __shared__ uint32_t hist[kRsBins];
+    if (cond && *cond == 0) keys = keys_alt;  // the conditional pass before this one did not run
     hist[threadIdx.x] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * kRsTile;
@@ -315,7 +327,17 @@ key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n
 __global__ void __launch_bounds__(kRsThreads, NFFT_SORT_MINB)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, long long n, int shift,
-                     const uint32_t* __restrict__ table_scanned, int nblocks) {
+                     const uint32_t* __restrict__ table_scanned, int nblocks,
+                     const uint32_t* __restrict__ cond = nullptr, int cond_mode = 0,
+                     const uint32_t* __restrict__ keys_alt = nullptr) {
+    // Conditional passes (Geom::mixed, see sort_points): cond_mode 1 = this pass runs only if *cond != 0;
+    // cond_mode 2 = the pass before this one was conditional: if it did not run, read its input instead
+    // (keys_alt, identity payload).
+    if (cond_mode == 1 && *cond == 0) return;
+    if (cond_mode == 2 && *cond == 0) {
+        keys_in = keys_alt;
+        idx_in = nullptr;
+    }
     __shared__ uint32_t wcnt[kRsWarps][kRsBins];
     __shared__ uint32_t s_key[kRsTile];
     __shared__ uint32_t s_idx[kRsTile];
@@ -386,6 +408,30 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     }
 }
 
+// Geom::mixed -- is the point set clustered?  Every `stride`-th key is counted into its tile; the set is
+// "clustered" (flag = 1) when at least 1/8 of the sampled points lie in tiles that hold >= dense_pts points.
+// Only then does the radix sort run its low pass over the fine key bits (which makes the chunks of a heavy tile
+// compact) and only then are heavy tiles marked for the 2 x 2 x 2 sweep (fill_items_kernel).
+__global__ void __launch_bounds__(256)
+density_sample_kernel(const uint32_t* __restrict__ keys, long long n, int stride, int fine_bits,
+                      uint32_t* __restrict__ counts) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    if (i < n) atomicAdd(&counts[keys[i] >> fine_bits], 1u);
+}
+__global__ void __launch_bounds__(1024)
+density_flag_kernel(const uint32_t* __restrict__ counts, long long nbins, int stride, int dense_pts, long long n,
+                    uint32_t* __restrict__ flag) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t heavy = 0;
+    for (long long b = threadIdx.x; b < nbins; b += 1024) {
+        const uint32_t c = counts[b];
+        if ((unsigned long long)c * stride >= (unsigned long long)dense_pts) heavy += c;
+    }
+    uint32_t total;
+    block_excl_scan(heavy, s_warp, &total);
+    if (threadIdx.x == 0) *flag = (unsigned long long)total * stride * 8ull >= (unsigned long long)n ? 1u : 0u;
+}
+
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* out, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)i;
@@ -404,18 +450,21 @@ chunk_count_kernel(const uint32_t* __restrict__ bin_start, long long nbins, int 
 // items[w] = {bin, first point, one past the last point, 0}: the points of a bin are split evenly
 // over its chunks.  Entries beyond the last work item stay zero (empty range), so a CTA needs one
 // 16-byte load to know its work.
+// items[].w = class of the tile (Geom::mixed): 1 = heavy (>= dense_pts points, and the keys were refined:
+// *refined != 0 or refined == nullptr), else 0.
 __global__ void __launch_bounds__(256)
 fill_items_kernel(const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ chunk_start, long long nbins,
-                  uint4* __restrict__ items) {
+                  uint4* __restrict__ items, int dense_pts = 0, const uint32_t* __restrict__ refined = nullptr) {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbins) return;
     const uint32_t lo = chunk_start[b], hi = chunk_start[b + 1];
     const uint32_t p0 = bin_start[b];
     const unsigned long long cnt = bin_start[b + 1] - p0;
     const uint32_t nch = hi - lo;
+    const uint32_t cls = dense_pts > 0 && cnt >= (unsigned long long)dense_pts && (!refined || *refined != 0) ? 1u : 0u;
     for (uint32_t w = lo; w < hi; ++w) {
         const uint32_t c = w - lo;
-        items[w] = make_uint4((uint32_t)b, p0 + (uint32_t)(cnt * c / nch), p0 + (uint32_t)(cnt * (c + 1) / nch), 0u);
+        items[w] = make_uint4((uint32_t)b, p0 + (uint32_t)(cnt * c / nch), p0 + (uint32_t)(cnt * (c + 1) / nch), cls);
     }
 }
 
@@ -572,16 +621,31 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
             NF_LAUNCH(key_tile_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, pos, bref, n, g, keys0, table,
                       (int)L.nblocks);
         }
+        // Geom::mixed with a refine pass: pass 0 covers fine key bits only and runs only for clustered point sets
+        // (device flag plan->flags[2], from a sample of the keys); pass 1 then reads either its output or, if it
+        // did not run, the unsorted keys with the identity payload.  A uniform point set pays the sampling and a
+        // few empty launches (~20 us at 2^24 points), not the pass (0.2 ms).
+        const bool refine = g.mixed && g.refine_pass && passes >= 2;
+        uint32_t* refined = plan->flags + 2;
+        if (refine) {
+            const int stride = n >= (1ll << 22) ? 32 : 8;
+            NF_CUDA(cudaMemsetAsync(nch, 0, (size_t)(nbins + 1) * 4, st));
+            const long long ns = (n + stride - 1) / stride;
+            NF_LAUNCH(density_sample_kernel, (unsigned)((ns + 255) / 256), 256, 0, st, keys0, n, stride, g.fine_bits, nch);
+            NF_LAUNCH(density_flag_kernel, 1, 1024, 0, st, nch, nbins, stride, g.dense_tile_pts, n, refined);
+        }
         for (int p = 0; p < passes; ++p) {
             uint32_t* kout = kbuf[p & 1];
             uint32_t* iout = ibuf[p & 1];
+            const bool cond_run = refine && p == 0, cond_in = refine && p == 1;
             if (p > 0) {
                 NF_LAUNCH(radix_hist_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, n, 8 * p, table,
-                          (int)L.nblocks);
+                          (int)L.nblocks, cond_in ? keys0 : nullptr, cond_in ? refined : nullptr);
             }
-            NF_TRY(scan_exclusive(table, table, kRsBins * L.nblocks, scan, st));
+            NF_TRY(scan_exclusive(table, table, kRsBins * L.nblocks, scan, st, cond_run ? refined : nullptr));
             NF_LAUNCH(radix_scatter_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, kin, iin, kout, iout, n, 8 * p,
-                      table, (int)L.nblocks);
+                      table, (int)L.nblocks, (cond_run || cond_in) ? refined : nullptr, cond_run ? 1 : (cond_in ? 2 : 0),
+                      cond_in ? keys0 : nullptr);
             kin = kout;
             iin = iout;
         }
@@ -601,7 +665,8 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
     NF_TRY(scan_exclusive(nch, chunk_start, nbins, scan, st));
     NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)plan->max_items * sizeof(uint4), st));
     NF_LAUNCH(fill_items_kernel, (unsigned)((nbins + 255) / 256), 256, 0, st, bin_start, chunk_start, nbins,
-              plan->items);
+              plan->items, g.mixed ? g.dense_tile_pts : 0,
+              g.mixed && g.refine_pass && sort_passes(g) >= 2 ? plan->flags + 2 : nullptr);
     return NFFTB200_OK;
 }
 

@@ -119,7 +119,8 @@ def _ptr(t):
 # persistent point plan (the reference recomputes its per-point scratch in
 # every call, core_cuda.cu:188-211, 461-484)
 # --------------------------------------------------------------------------------------
-_TILING_FIELDS = ("dim", "M", "Tx", "Ty", "Tz", "ntx", "nty", "ntz", "pmax", "fine_bits", "scx", "scy", "scz")
+_TILING_FIELDS = ("dim", "M", "Tx", "Ty", "Tz", "ntx", "nty", "ntz", "pmax", "fine_bits", "scx", "scy", "scz", "mixed",
+                  "dense_tile_pts")
 
 
 class NfftPlan:
@@ -185,10 +186,12 @@ class NfftPlan:
     def flags(self):
         """Device-side counters of the binnings made so far, summed: `dropped` = points that transforms using this
         plan found outside their tile (evidence that the positions changed after the plan was made), `tma_timeouts`
-        = TMA tile loads that did not complete (must be 0).  Reads device memory: synchronises the current stream."""
+        = TMA tile loads that did not complete (must be 0), `clustered` = binnings that found the point set clustered
+        and marked its heavy tiles for the 2 x 2 x 2 sweep (large 3D sets).  Reads device memory: synchronises the
+        current stream."""
         import ctypes
         L = _lib.lib()
-        dropped = timeouts = 0
+        dropped = timeouts = clustered = 0
         out = (ctypes.c_uint32 * 8)()
         with torch.cuda.device(self.device):
             for buf, args in self._sorts.values():
@@ -196,7 +199,8 @@ class NfftPlan:
                                                  _stream_ptr(self.device)), "plan_flags")
                 dropped += int(out[0])
                 timeouts += int(out[1])
-        return {"dropped": dropped, "tma_timeouts": timeouts}
+                clustered += int(out[2])
+        return {"dropped": dropped, "tma_timeouts": timeouts, "clustered": clustered}
 
     def dropped_points(self):
         """Points that transforms using this plan found outside their tile (see `flags`).  Synchronises."""
