@@ -185,6 +185,10 @@ int nfftb200_profile_read(double* ms_out, int64_t* count_out);
 /* Tests: force the 64-bit index variants of the spectral kernels (normally chosen when B*C*M^d >= 2^31). */
 void nfftb200_debug_force_int64(int on);
 
+/* Tests: the smallest number of resident CTAs per SM the runtime reported for any launch configuration of the 3D
+ * register-stencil sweeps so far (they are built for 2; -1 = none launched yet). */
+int nfftb200_debug_min_resident_ctas(void);
+
 /* Tests / experiments: mixed-density mode of the 3D register-stencil path (heavy tiles swept with 2 x 2 x 2
  * supercells, decided on the device).  mode -1 = default, 0 = off, 1 = on; min_points = smallest point set
  * that uses it (-1 = default 2^20); dense_tile_pts = points that make a 16^3 tile heavy (<= 0 = default 8192). */

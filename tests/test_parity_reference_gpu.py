@@ -25,6 +25,7 @@ from conftest import ROOT
 from fullsize_cases import CASES, make_case
 from oracle import nfft_oracle as O
 import torch_nfft_b200 as T
+from torch_nfft_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -79,6 +80,14 @@ def test_pair_matches_reference_at_baseline_size(name):
            reference_run_to_run=ref["run_to_run"], reference_seconds=ref["seconds"], tol=TOL)
     assert y.shape == ref["y"].shape and f.shape == ref["f"].shape
     assert e_adj <= TOL and e_fwd <= TOL and e_chain <= TOL, (e_adj, e_fwd, e_chain)
+    if name.startswith("c4"):
+        # 3D sweeps: two CTAs per SM must fit (shared memory), and the device-side density decision must find
+        # the clustered set (its heavy tiles are then swept with 2 x 2 x 2 supercells) and only that one
+        assert _lib.lib().nfftb200_debug_min_resident_ctas() == 2
+        plan = T.NfftPlan(pos, batch)
+        y3 = T.nfft_adjoint(x, plan=plan, N=c["N"], m=c["m"])
+        assert rel(y3.cpu(), ref["y"]) <= TOL
+        assert plan.flags() == {"dropped": 0, "tma_timeouts": 0, "clustered": 1 if name == "c4_clustered" else 0}
 
 
 def test_fastsum_matches_reference_at_c5_density():

@@ -378,7 +378,11 @@ static WindowKernel get_gather(int dim, int ncomp, int L) {
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) and size, not per launch
 static std::mutex g_attr_mutex;
 static std::map<std::pair<int, const void*>, size_t> g_attr_smem;
-static int ensure_dynamic_smem(const void* kern, size_t smem) {
+// threads > 0: the kernel is built for TWO resident CTAs per SM (the 3D register-stencil sweeps); the smallest
+// number the runtime reports for any such launch configuration is kept for nfftb200_debug_min_resident_ctas --
+// the sweeps sit within a few hundred bytes of the shared-memory limit and losing the second CTA costs 45 %.
+static std::atomic<int> g_min_resident{1 << 30};
+static int ensure_dynamic_smem(const void* kern, size_t smem, int threads = 0) {
     if (smem > 227 * 1024) NF_FAIL(NFFTB200_ERR_INVALID, "tile needs %zu bytes of shared memory", smem);
     int dev = 0;
     NF_CUDA(cudaGetDevice(&dev));
@@ -387,6 +391,11 @@ static int ensure_dynamic_smem(const void* kern, size_t smem) {
     if (smem > have) {
         NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
+        if (threads > 0) {
+            int ctas = 0;
+            NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, threads, smem));
+            if (ctas < g_min_resident.load()) g_min_resident.store(ctas);
+        }
     }
     return NFFTB200_OK;
 }
@@ -495,15 +504,12 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
     if (g.use_reg == 1) {
         // supercell kRegSX x kRegSY x kRegSZ = 4 x 4 x 2 cells; for m = 4 the register block is 13 x 13 x 12:
         // 6 positions x 6 float2 accumulators per lane
-        // mixed density: both sweeps are launched, each takes the work items of its class of tiles
-        const int nsweeps = g.mixed ? 2 : 1;
-        for (int sweep = 0; sweep < nsweeps; ++sweep) {
         WindowKernelTma kern = nullptr;
         int win_floats = 0;
-        // 2 x 2 x 2 supercells: dense point sets (m = 3, 4), or the heavy tiles of a mixed set
-        const bool small_cells = g.mixed ? sweep == 1 : (g.sc[0] == 2 && g.sc[1] == 2 && g.sc[2] == 2);
+        // 2 x 2 x 2 supercells: dense point sets (m = 3, 4).  Mixed density: ONE launch whose CTAs choose the sweep
+        // by the class of their work item (spread/gather_reg_mixed_kernel); shared memory for the larger of the two.
+        const bool small_cells = g.sc[0] == 2 && g.sc[1] == 2 && g.sc[2] == 2;
         const int scx = small_cells ? 2 : kRegSX, scy = small_cells ? 2 : kRegSY, scz = small_cells ? 2 : kRegSZ;
-        a.item_sel = g.mixed ? 1 + sweep : 0;
         switch (g.m) {
 #define NF_REG_CASE(M_, L_)                                                                          \
             case M_:                                                                                 \
@@ -513,7 +519,12 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
                 break;
 #define NF_REG_CASE_DENSE(M_, L_)                                                                    \
             case M_:                                                                                 \
-                if (small_cells) {                                                                   \
+                if (g.mixed) {                                                                       \
+                    kern = spread ? spread_reg_mixed_kernel<L_> : gather_reg_mixed_kernel<L_>;       \
+                    win_floats = RegCfg<L_, 2, 2, 2>::WIN_FLOATS;                                    \
+                    if (win_floats < RegCfg<L_, kRegSX, kRegSY, kRegSZ>::WIN_FLOATS)                 \
+                        win_floats = RegCfg<L_, kRegSX, kRegSY, kRegSZ>::WIN_FLOATS;                 \
+                } else if (small_cells) {                                                            \
                     kern = spread ? spread_reg_kernel<L_, 2, 2, 2> : gather_reg_kernel<L_, 2, 2, 2>; \
                     win_floats = RegCfg<L_, 2, 2, 2>::WIN_FLOATS;                                    \
                 } else {                                                                             \
@@ -534,13 +545,12 @@ static int launch_window(bool spread, const Geom& g, WindowArgs a, const SortPla
         // experiment switch: NFFTB200_SMEM_PAD=<bytes> requests more shared memory per CTA (fewer resident CTAs)
         static const size_t smem_pad = getenv("NFFTB200_SMEM_PAD") ? (size_t)atoll(getenv("NFFTB200_SMEM_PAD")) : 0;
         const size_t smem = reg_smem_bytes(g, nsc, win_floats) + smem_pad;
-        NF_TRY(ensure_dynamic_smem((const void*)kern, smem));
+        NF_TRY(ensure_dynamic_smem((const void*)kern, smem, smem_pad ? 0 : kRegThreads));
         CUtensorMap tmap;
         a.use_tma = make_grid_tensor_map(g, a.grid, &tmap) ? 1 : 0;
         for (int k0 = 0; k0 < g.K; ++k0) {
             a.k0 = k0;
             NF_LAUNCH(kern, (unsigned)sp.max_items, kRegThreads, smem, st, g, a, tmap);
-        }
         }
         return NFFTB200_OK;
     }
@@ -910,6 +920,11 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
 }
 
 void nfftb200_debug_force_int64(int on) { g_force_int64.store(on ? 1 : 0); }
+
+int nfftb200_debug_min_resident_ctas(void) {
+    const int v = g_min_resident.load();
+    return v == (1 << 30) ? -1 : v;
+}
 
 void nfftb200_debug_mixed(int mode, int64_t min_points, int dense_tile_pts) {
     g_mixed_mode.store(mode < 0 ? -1 : (mode ? 1 : 0));

@@ -299,7 +299,8 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uin
 // (saves re-reading the keys in radix_hist_kernel).
 __global__ void __launch_bounds__(kRsThreads)
 key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n, Geom g,
-                uint32_t* __restrict__ keys, uint32_t* __restrict__ table, int nblocks) {
+                uint32_t* __restrict__ keys, uint32_t* __restrict__ table, int nblocks,
+                uint32_t* __restrict__ sample_counts = nullptr, int sample_mask = 0) {
     __shared__ uint32_t hist[kRsBins];
     hist[threadIdx.x] = 0;
     __syncthreads();
@@ -312,6 +313,8 @@ key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n
             const uint32_t key = point_key(pos, batch, i, g, f);
             keys[i] = key;
             atomicAdd(&hist[key & 255u], 1u);
+            // Geom::mixed: every (sample_mask + 1)-th point is counted into its tile (see density_flag_kernel)
+            if (sample_counts && (i & sample_mask) == 0) atomicAdd(&sample_counts[key >> g.fine_bits], 1u);
         }
     }
     __syncthreads();
@@ -408,16 +411,10 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     }
 }
 
-// Geom::mixed -- is the point set clustered?  Every `stride`-th key is counted into its tile; the set is
+// Geom::mixed -- is the point set clustered?  Every `stride`-th key is counted into its tile (key_tile_kernel); the set is
 // "clustered" (flag = 1) when at least 1/8 of the sampled points lie in tiles that hold >= dense_pts points.
 // Only then does the radix sort run its low pass over the fine key bits (which makes the chunks of a heavy tile
 // compact) and only then are heavy tiles marked for the 2 x 2 x 2 sweep (fill_items_kernel).
-__global__ void __launch_bounds__(256)
-density_sample_kernel(const uint32_t* __restrict__ keys, long long n, int stride, int fine_bits,
-                      uint32_t* __restrict__ counts) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * stride;
-    if (i < n) atomicAdd(&counts[keys[i] >> fine_bits], 1u);
-}
 __global__ void __launch_bounds__(1024)
 density_flag_kernel(const uint32_t* __restrict__ counts, long long nbins, int stride, int dense_pts, long long n,
                     uint32_t* __restrict__ flag) {
@@ -603,11 +600,18 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
     uint32_t* table = (uint32_t*)(scratch + L.table);
     uint32_t* scan = (uint32_t*)(scratch + L.scan);
     const BatchRef bref{batch, batch_is_offsets ? g.B : 0};
+    const int sample_stride = n >= (1ll << 22) ? 32 : 8;  // power of two
 
     // single radix pass whose digit is the bin (small problems): one finishing launch, no memsets
     const bool single_pass = n > 0 && passes == 1 && g.fine_bits == 0 && nbins <= kRsBins;
+    // Geom::mixed with a refine pass: pass 0 covers fine key bits only and runs only for clustered point sets
+    // (device flag plan->flags[2], from a sample of the keys counted per tile into `nch`); pass 1 then reads
+    // either its output or, if it did not run, the unsorted keys with the identity payload.  A uniform point set
+    // pays the sampling and a few empty launches, not the pass (0.2 ms at 2^24 points).
+    const bool refine = g.mixed && g.refine_pass && passes >= 2 && n > 0;
     if (!single_pass) {
-        NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, st));
+        // bin_count (and, right behind it, the sample counts in nch) = 0
+        NF_CUDA(cudaMemsetAsync(bin_count, 0, (refine ? L.nch - L.bin_count : 0) + (size_t)(nbins + 1) * 4, st));
         NF_CUDA(cudaMemsetAsync(plan->flags, 0, kPlanFlagWords * 4, st));
     }
     // stable LSD radix sort of (key, index) over the key bits that can be set
@@ -619,21 +623,11 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
             NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, plan->perm, n);
         } else {
             NF_LAUNCH(key_tile_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, pos, bref, n, g, keys0, table,
-                      (int)L.nblocks);
+                      (int)L.nblocks, refine ? nch : nullptr, sample_stride - 1);
         }
-        // Geom::mixed with a refine pass: pass 0 covers fine key bits only and runs only for clustered point sets
-        // (device flag plan->flags[2], from a sample of the keys); pass 1 then reads either its output or, if it
-        // did not run, the unsorted keys with the identity payload.  A uniform point set pays the sampling and a
-        // few empty launches (~20 us at 2^24 points), not the pass (0.2 ms).
-        const bool refine = g.mixed && g.refine_pass && passes >= 2;
         uint32_t* refined = plan->flags + 2;
-        if (refine) {
-            const int stride = n >= (1ll << 22) ? 32 : 8;
-            NF_CUDA(cudaMemsetAsync(nch, 0, (size_t)(nbins + 1) * 4, st));
-            const long long ns = (n + stride - 1) / stride;
-            NF_LAUNCH(density_sample_kernel, (unsigned)((ns + 255) / 256), 256, 0, st, keys0, n, stride, g.fine_bits, nch);
-            NF_LAUNCH(density_flag_kernel, 1, 1024, 0, st, nch, nbins, stride, g.dense_tile_pts, n, refined);
-        }
+        if (refine)
+            NF_LAUNCH(density_flag_kernel, 1, 1024, 0, st, nch, nbins, sample_stride, g.dense_tile_pts, n, refined);
         for (int p = 0; p < passes; ++p) {
             uint32_t* kout = kbuf[p & 1];
             uint32_t* iout = ibuf[p & 1];

@@ -38,7 +38,6 @@ struct WindowArgs {
     uint32_t* flags;         // point plan flags: flags[0] counts points found outside their tile (stale plan),
                              // flags[1] TMA transfers that did not complete (must stay 0)
     int use_tma;             // 3D register-stencil kernels: tile planes move by TMA (window_reg.cuh)
-    int item_sel;            // 0: all work items; 1 + c: only the items of class c (items[].w, Geom::mixed)
 };
 
 // a point of a work item lies outside the item's tile: the plan was made for other positions
@@ -159,13 +158,14 @@ __device__ __forceinline__ float4 load_quad(const Geom& g, const float* grid, in
 struct TileCtx {
     int b, org[3];
     long long p_lo, p_hi;
+    int cls;  // class of the tile (items[].w; Geom::mixed: 1 = heavy tile)
 };
 
 __device__ __forceinline__ bool decode_item(const Geom& g, const WindowArgs& a, TileCtx& t) {
     const uint4 it = __ldg(a.items + blockIdx.x);
     if (it.y == it.z) return false;  // beyond the last work item
-    if (a.item_sel && (int)it.w + 1 != a.item_sel) return false;  // another kernel's class of tiles
     const int bin = (int)it.x;
+    t.cls = (int)it.w;
     t.p_lo = it.y;
     t.p_hi = it.z;
     t.b = bin / g.tiles_per_batch;

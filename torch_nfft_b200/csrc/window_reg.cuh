@@ -538,7 +538,21 @@ __device__ __forceinline__ void order_columns(const int* s_start, int ncols, int
 #ifndef NFFT_REG_UNITS
 #define NFFT_REG_UNITS (2 * kRegWarps)  // units a chunk is cut into when its columns are uneven
 #endif
-constexpr int kRegMaxUnits = 128;  // >= NFFT_REG_UNITS + columns of a tile (16 with 4 x 4, 64 with 2 x 2 supercells)
+constexpr int kRegMaxUnits = 96;  // >= NFFT_REG_UNITS + columns of a tile (16 with 4 x 4, 64 with 2 x 2 supercells)
+static_assert(kRegMaxUnits >= NFFT_REG_UNITS + 64, "unit list: one per column plus the extra segments");
+// Static shared memory of the 3D sweeps, declared ONCE in a non-template function: a kernel that carries two sweeps
+// (spread/gather_reg_mixed_kernel) must not allocate it twice -- at c4 two CTAs of 114 KB dynamic shared memory
+// share an SM with 2.7 KB to spare.
+struct RegStatic {
+    unsigned long long mbar;                             // gather: TMA tile load
+    int expect[32], done[32], tma[kTmaParamWords];       // spread: TMA flush bookkeeping per plane pair
+    int lock[64];                                        // spread: one lock per pair of tile planes
+    int order[kRegMaxUnits], nunits, next;               // work units of the CTA, hand-out counter
+};
+__device__ __forceinline__ RegStatic& reg_static() {
+    __shared__ __align__(8) RegStatic s;
+    return s;
+}
 static_assert(kRegMaxPts < 4096, "unit encoding: 12 bits per point position");
 static_assert(kRegMaxPts % 16 == 0, "the tap windows behind the u8 offsets must stay 16-byte aligned");
 // s_expect (spread with the TMA flush, else nullptr): s_expect[p] = number of units that will add into plane
@@ -723,13 +737,11 @@ __device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const f
 // spread
 // ======================================================================================
 template <int LC, int SX, int SY, int SZ>
-__global__ void __launch_bounds__(kRegThreads, 2)
-spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
+__device__ __forceinline__ void spread_reg_body(const Geom& g, const WindowArgs& a, const CUtensorMap* tmap,
+                                                const TileCtx& t) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
     constexpr int WX = Cfg::WX, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
     extern __shared__ __align__(128) float smem_reg[];
-    TileCtx t;
-    if (!decode_item(g, a, t)) return;
     NFFT_PHASE_MARK(ph0);
     NFFT_PHASE_BEGIN(0);
 
@@ -737,7 +749,9 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     const int nsc = nsx * nsy * nsz;
     float* tile = align_tile(smem_reg);
     // TMA flush: plane pairs leave for the grid as soon as every unit that adds into them has done so
-    __shared__ int s_expect[32], s_done[32], s_tma[kTmaParamWords];
+    RegStatic& S = reg_static();
+    int *s_expect = S.expect, *s_done = S.done, *s_tma = S.tma, *s_lock = S.lock, *s_order = S.order;
+    int &s_next = S.next, &s_nunits = S.nunits;
     const int npairs = (g.P[2] + 1) / 2;
     if (threadIdx.x < 32) s_expect[threadIdx.x] = 0, s_done[threadIdx.x] = 0;
     // Only tiles that lie inside the grid in X and Y: a box with a NEGATIVE start coordinate raises "illegal
@@ -760,14 +774,11 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     float* s_win = reinterpret_cast<float*>(s_off + kRegMaxPts);
     int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
     int* s_cur = s_start + nsc + 2;
-    __shared__ int s_next;
-    __shared__ int s_lock[64];  // one lock per pair of tile planes
     if (threadIdx.x < 64) s_lock[threadIdx.x] = 0;
 
     for (int i = threadIdx.x; i < (g.tile_elems >> 2); i += kRegThreads)  // tile_elems is a multiple of 4
         reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    __shared__ int s_order[kRegMaxUnits], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     __syncthreads();
     NFFT_PHASE_MARK(pha);
@@ -883,7 +894,7 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
                         // it again); the sweep goes on while the reduction drains
                         const int pr = scz * SP + kp;
                         if (tma_tile && atomicAdd(&s_done[pr], 1) + 1 == s_expect[pr])
-                            tma_flush_plane_pair(&tmap, (uint32_t)__cvta_generic_to_shared(tile), s_tma, pr, g.P[2], g.sZ,
+                            tma_flush_plane_pair(tmap, (uint32_t)__cvta_generic_to_shared(tile), s_tma, pr, g.P[2], g.sZ,
                                                  g.M);
                     }
                 }
@@ -1002,24 +1013,43 @@ spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     NFFT_PHASE_END(0, ph0, ph4, cnt);
 }
 
+template <int LC, int SX, int SY, int SZ>
+__global__ void __launch_bounds__(kRegThreads, 2)
+spread_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+    spread_reg_body<LC, SX, SY, SZ>(g, a, &tmap, t);
+}
+// Geom::mixed: one launch, the sweep is chosen per work item -- heavy tiles (class 1, marked by the binning when
+// the point set was found clustered) with 2 x 2 x 2 supercells, the others with the default supercell.
+template <int LC>
+__global__ void __launch_bounds__(kRegThreads, 2)
+spread_reg_mixed_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+    if (t.cls) spread_reg_body<LC, 2, 2, 2>(g, a, &tmap, t);
+    else spread_reg_body<LC, kRegSX, kRegSY, kRegSZ>(g, a, &tmap, t);
+}
+
 // ======================================================================================
 // gather
 // ======================================================================================
 template <int LC, int SX, int SY, int SZ>
-__global__ void __launch_bounds__(kRegThreads, 2)
-gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
+__device__ __forceinline__ void gather_reg_body(const Geom& g, const WindowArgs& a, const CUtensorMap* tmap,
+                                                const TileCtx& t) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
     constexpr int WX = Cfg::WX, WZ = Cfg::WZ, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
     extern __shared__ __align__(128) float smem_reg[];
-    TileCtx t;
-    if (!decode_item(g, a, t)) return;
     NFFT_PHASE_MARK(ph0);
     NFFT_PHASE_BEGIN(1);
 
     const int nsx = (g.T[0] + SX - 1) / SX, nsy = (g.T[1] + SY - 1) / SY, nsz = (g.T[2] + SZ - 1) / SZ;
     const int nsc = nsx * nsy * nsz;
     float* tile = align_tile(smem_reg);
-    __shared__ __align__(8) unsigned long long s_mbar;
+    RegStatic& S = reg_static();
+    unsigned long long& s_mbar = S.mbar;
+    int* s_order = S.order;
+    int &s_next = S.next, &s_nunits = S.nunits;
     // planes by TMA unless the tile crosses the periodic boundary in X or Y (a load zero-fills out-of-range
     // elements, which would overwrite the wrapped half; the Z wrap is per plane)
     const bool tma_tile = a.use_tma && t.org[0] >= 0 && t.org[0] + g.P[0] <= g.M && t.org[1] >= 0 && t.org[1] + g.P[1] <= g.M;
@@ -1030,10 +1060,8 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     float* s_win = reinterpret_cast<float*>(s_off + kRegMaxPts);
     int* s_start = reinterpret_cast<int*>(s_win + kRegWarps * Cfg::WIN_FLOATS);
     int* s_cur = s_start + nsc + 2;
-    __shared__ int s_next;
 
     for (int i = threadIdx.x; i < nsc; i += kRegThreads) s_cur[i] = 0;
-    __shared__ int s_order[kRegMaxUnits], s_nunits;
     if (threadIdx.x == 0) s_next = 0, s_nunits = 0;
     // stage the padded tile (periodic wrap resolved per quad)
     // the tile travels with asynchronous copies while the points are loaded and bucketed (both phases
@@ -1048,7 +1076,7 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
             for (int zz = 0; zz < g.P[2]; ++zz) {
                 int gz = t.org[2] + zz;
                 gz = gz < 0 ? gz + g.M : (gz >= g.M ? gz - g.M : gz);
-                tma_load_plane(tile_s + 4u * (uint32_t)(zz * g.sZ), &tmap, mbar, t.org[0], t.org[1], gz, plane);
+                tma_load_plane(tile_s + 4u * (uint32_t)(zz * g.sZ), tmap, mbar, t.org[0], t.org[1], gz, plane);
             }
         }
     } else {
@@ -1255,6 +1283,22 @@ gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUte
     NFFT_PHASE_ADD(1, 2, ph2, ph3);
     NFFT_PHASE_ADD(1, 4, 0, 1);
     NFFT_PHASE_END(1, ph0, ph3, cnt);
+}
+
+template <int LC, int SX, int SY, int SZ>
+__global__ void __launch_bounds__(kRegThreads, 2)
+gather_reg_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+    gather_reg_body<LC, SX, SY, SZ>(g, a, &tmap, t);
+}
+template <int LC>
+__global__ void __launch_bounds__(kRegThreads, 2)
+gather_reg_mixed_kernel(const Geom g, const WindowArgs a, const __grid_constant__ CUtensorMap tmap) {  // see the spread
+    TileCtx t;
+    if (!decode_item(g, a, t)) return;
+    if (t.cls) gather_reg_body<LC, 2, 2, 2>(g, a, &tmap, t);
+    else gather_reg_body<LC, kRegSX, kRegSY, kRegSZ>(g, a, &tmap, t);
 }
 
 }  // namespace nfftb200
