@@ -63,6 +63,11 @@ extern "C" {
                                   /* sort regions (also a flag of nfftb200_workspace_bytes)   */
 #define NFFTB200_BATCH_OFFSETS 32 /* the `batch` pointers are B+1 ascending int64 OFFSETS of  */
                                   /* the point sets (CSR style) instead of one entry per point */
+#define NFFTB200_CLUSTERED 64     /* hint: the points are clustered (large 3D sets, m = 3, 4).  */
+                                  /* The binning then samples the keys on the device and, if it  */
+                                  /* finds heavy tiles, refines the sort and marks their work    */
+                                  /* items for the 2 x 2 x 2-supercell sweep.  Part of the        */
+                                  /* geometry: a plan and the calls that use it must agree on it */
 
 int nfftb200_version(void);
 const char* nfftb200_last_error(void);
@@ -191,7 +196,7 @@ int nfftb200_debug_min_resident_ctas(void);
 
 /* Tests / experiments: mixed-density mode of the 3D register-stencil path (heavy tiles swept with 2 x 2 x 2
  * supercells, decided on the device).  mode -1 = default, 0 = off, 1 = on; min_points = smallest point set
- * that uses it (-1 = default 2^20); dense_tile_pts = points that make a 16^3 tile heavy (<= 0 = default 8192). */
+ * that uses it (-1 = default 2^18); dense_tile_pts = points that make a 16^3 tile heavy (<= 0 = default 2048). */
 void nfftb200_debug_mixed(int mode, int64_t min_points, int dense_tile_pts);
 
 /* cuFFT plan cache: an LRU of handles per (device, dimension, M, type, B*C).  _clear destroys them (all

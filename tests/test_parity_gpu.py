@@ -571,13 +571,13 @@ def test_cuda_graph_capture_and_replay(d, N, m, B, n):
 
 
 # ---------------------------------------------------------------------------------------------
-# mixed density (large 3D point sets): whether the set is clustered is decided on the device from a sample of
-# the keys; heavy tiles are then swept with 2 x 2 x 2 supercells, the rest with 4 x 4 x 2
+# mixed density (large 3D point sets with the CLUSTERED hint): whether the set really is clustered is decided on
+# the device from a sample of the keys; heavy tiles are then swept with 2 x 2 x 2 supercells, the rest with 4 x 4 x 2
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture
 def mixed_mode():
     L = _lib.lib()
-    L.nfftb200_debug_mixed(1, 0, 600)  # on for every size; a 16^3 tile is heavy from 600 points
+    L.nfftb200_debug_mixed(-1, 0, 600)  # hinted sets of every size; a 16^3 tile is heavy from 600 points
     yield
     L.nfftb200_debug_mixed(-1, -1, 0)
 
@@ -603,8 +603,9 @@ def clustered_points(rng, n, B, sigma=0.03, uniform_share=0.2):
 def test_mixed_density_transforms(mixed_mode, m, cplx):
     rng = np.random.default_rng(40 + m)
     N, B, n = 32, 2, 15000
-    geo = _lib.geometry(3, N, m, B, 1, 0, B * n)
+    geo = _lib.geometry(3, N, m, B, 1, _lib.CLUSTERED, B * n)
     assert geo["mixed"] == 1 and geo["refine_pass"] == 1 and geo["dense_tile_pts"] == 600
+    assert _lib.geometry(3, N, m, B, 1, 0, B * n)["mixed"] == 0  # no hint: the single-sweep path
     for clustered in (True, False):
         if clustered:
             pos, batch = clustered_points(rng, n, B)
@@ -612,7 +613,7 @@ def test_mixed_density_transforms(mixed_mode, m, cplx):
             pos, batch = make_points(rng, 3, B, n)
         x = make_values(rng, (pos.shape[0],), cplx)
         tp, tb, tx = cuda(pos), cuda(batch), cuda(x)
-        plan = T.NfftPlan(tp, tb)
+        plan = T.NfftPlan(tp, tb, clustered=True)
         y = T.nfft_adjoint(tx, plan=plan, N=N, m=m)
         ref_y = O.nfft_adjoint(x, pos, batch, N, m)
         assert O.rel_l2(y.cpu().numpy(), ref_y) < TOL
@@ -620,12 +621,15 @@ def test_mixed_density_transforms(mixed_mode, m, cplx):
         assert O.rel_l2(f.cpu().numpy(), O.nfft_forward(ref_y, pos, batch, m)) < TOL
         # the device-side decision: heavy tiles exist only in the clustered set
         assert plan.flags() == {"dropped": 0, "tma_timeouts": 0, "clustered": 1 if clustered else 0}
-        # the same transforms without a kept plan, and against the single-sweep path
-        y1 = T.nfft_adjoint(tx, tp, tb, N, m)
-        _lib.lib().nfftb200_debug_mixed(0, 0, 0)
+        # against the single-sweep path (no hint)
         y0 = T.nfft_adjoint(tx, tp, tb, N, m)
-        _lib.lib().nfftb200_debug_mixed(1, 0, 600)
-        assert O.rel_l2(y1.cpu().numpy(), ref_y) < TOL and O.rel_l2(y0.cpu().numpy(), y1.cpu().numpy()) < 2e-6
+        assert O.rel_l2(y0.cpu().numpy(), y.cpu().numpy()) < 2e-6
+        # fastsum through the same plan (symmetric: one binning for spread and gather)
+        if not cplx and clustered:
+            coeffs = cuda(make_values(rng, (N, N, N), False))
+            s1 = T.nfft_fastsum(tx, coeffs, tp, batch=tb, cutoff=m, source_plan=plan)
+            s0 = T.nfft_fastsum(tx, coeffs, tp, batch=tb, cutoff=m)
+            assert O.rel_l2(s1.cpu().numpy(), s0.cpu().numpy()) < 2e-6
 
 
 def test_mixed_density_binning_is_bit_exact(mixed_mode):
@@ -640,14 +644,14 @@ def test_mixed_density_binning_is_bit_exact(mixed_mode):
         keys = torch.zeros(nn, dtype=torch.int32, device=DEV)
         perm = torch.zeros(nn, dtype=torch.int32, device=DEV)
         tile = (ctypes.c_int32 * 3)()
-        nb = L.nfftb200_workspace_bytes(_lib.OP_SORT, nn, 0, 3, N, m, B, 1, 0)
+        nb = L.nfftb200_workspace_bytes(_lib.OP_SORT, nn, 0, 3, N, m, B, 1, _lib.CLUSTERED)
         ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
         tp, tb = cuda(pos), cuda(batch)
         _lib.check(L.nfftb200_sort_points(tp.data_ptr(), tb.data_ptr(), keys.data_ptr(), perm.data_ptr(),
-                                          ctypes.cast(tile, ctypes.c_void_p), nn, 3, N, m, B, 1, 0, ws.data_ptr(),
-                                          ws.numel(), torch.cuda.current_stream().cuda_stream), "sort")
+                                          ctypes.cast(tile, ctypes.c_void_p), nn, 3, N, m, B, 1, _lib.CLUSTERED,
+                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "sort")
         torch.cuda.synchronize()
-        geo = _lib.geometry(3, N, m, B, 1, 0, nn)
+        geo = _lib.geometry(3, N, m, B, 1, _lib.CLUSTERED, nn)
         assert geo["mixed"] == 1 and geo["fine_bits"] == 9 and (geo["scx"], geo["scy"], geo["scz"]) == (2, 2, 2)
         okeys = O.sort_keys(pos, batch, N, list(tile)[::-1], geo["fine_bits"], (2, 2, 2))
         assert np.array_equal(keys.cpu().numpy().astype(np.int64), okeys)

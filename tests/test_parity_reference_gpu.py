@@ -84,9 +84,10 @@ def test_pair_matches_reference_at_baseline_size(name):
         # 3D sweeps: two CTAs per SM must fit (shared memory), and the device-side density decision must find
         # the clustered set (its heavy tiles are then swept with 2 x 2 x 2 supercells) and only that one
         assert _lib.lib().nfftb200_debug_min_resident_ctas() == 2
-        plan = T.NfftPlan(pos, batch)
+        plan = T.NfftPlan(pos, batch, clustered=True)  # the hint: sample the keys, decide per tile
         y3 = T.nfft_adjoint(x, plan=plan, N=c["N"], m=c["m"])
-        assert rel(y3.cpu(), ref["y"]) <= TOL
+        f3 = T.nfft_forward(ref["y"].to(dev), plan=plan, m=c["m"], real_output=True)
+        assert rel(y3.cpu(), ref["y"]) <= TOL and rel(f3.cpu(), ref["f"]) <= TOL
         assert plan.flags() == {"dropped": 0, "tma_timeouts": 0, "clustered": 1 if name == "c4_clustered" else 0}
 
 

@@ -13,7 +13,7 @@ from ._build import LIB_PATH as _DEFAULT_LIB_PATH
 LIB_PATH = os.environ.get("NFFTB200_LIB", _DEFAULT_LIB_PATH)
 
 OP_ADJOINT, OP_FORWARD, OP_FASTSUM, OP_SPREAD, OP_GATHER, OP_SORT, OP_SPECTRAL, OP_PLAN = range(8)
-X_COMPLEX, Y_REAL, COEFFS_COMPLEX, SYMMETRIC, PLANNED, BATCH_OFFSETS = 1, 2, 4, 8, 16, 32
+X_COMPLEX, Y_REAL, COEFFS_COMPLEX, SYMMETRIC, PLANNED, BATCH_OFFSETS, CLUSTERED = 1, 2, 4, 8, 16, 32, 64
 
 _lock = threading.Lock()
 _lib = None

@@ -171,15 +171,19 @@ static int sm_count() {
     return v;
 }
 
-// Mixed-density mode of the 3D register-stencil path (make_geom): -1 = default (on unless NFFTB200_NO_MIXED /
-// NFFTB200_NO_DENSE), 0 = off, 1 = on; point sets below g_mixed_min_points never use it (two sweeps are launched
-// and the keys are sampled: not worth it for small sets).  Test hook: nfftb200_debug_mixed.
+// Mixed-density mode of the 3D register-stencil path (make_geom): -1 = default (on for calls that carry
+// NFFTB200_CLUSTERED, or all calls with the environment variable NFFTB200_MIXED; never with NFFTB200_NO_MIXED /
+// NFFTB200_NO_DENSE), 0 = off, 1 = on; point sets below g_mixed_min_points never use it (the keys are sampled and
+// a conditional radix pass is launched: not worth it for small sets).  Test hook: nfftb200_debug_mixed.
 static std::atomic<int> g_mixed_mode{-1};
-static std::atomic<long long> g_mixed_min_points{1ll << 20};
+static std::atomic<long long> g_mixed_min_points{1ll << 18};
 static std::atomic<int> g_mixed_dense_pts{0};  // 0: kDenseTilePts / NFFTB200_DENSE_TILE_PTS
-constexpr int kDenseTilePts = 8192;  // 2 points per oversampled cell of a 16^3 tile
+constexpr int kDenseTilePts = 2048;  // half a point per oversampled cell of a 16^3 tile (profiles/r02r_ab.txt)
 
-static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, bool cplx, int64_t n_points) {
+// gflags: bit 0 = the grid is complex, bit 1 = the caller expects CLUSTERED points (NFFTB200_CLUSTERED)
+static inline int geom_flags(bool grid_cplx, int flags) { return (grid_cplx ? 1 : 0) | ((flags & NFFTB200_CLUSTERED) ? 2 : 0); }
+static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, int gflags, int64_t n_points) {
+    const bool cplx = gflags & 1, clustered_hint = gflags & 2;
     if (d < 1 || d > 3) NF_FAIL(NFFTB200_ERR_INVALID, "dimension d=%d not in [1,3]", d);
     if (N < 2 || (N & 1)) NF_FAIL(NFFTB200_ERR_INVALID, "bandwidth N=%lld must be even and >= 2", (long long)N);
     if (m < 1 || m > kMaxCutoff) NF_FAIL(NFFTB200_ERR_INVALID, "cutoff m=%d not in [1,%d]", m, kMaxCutoff);
@@ -259,8 +263,10 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     // * Fine key bits (sort.cuh: fine_index): the bits that fit the radix passes the tile key needs anyway are
     //   free; a dense set gets at least 4 of them even if that adds a pass, because its tiles are cut into many
     //   chunks and compact chunks are what lets the points of a chunk share register blocks.
-    // * Mixed density (everything else that is large enough): whether a point set is CLUSTERED is not known on
-    //   the host, so it is decided on the device, per tile.  The keys carry the 2 x 2 x 2 hierarchy, laid out so
+    // * Mixed density (large point sets the caller marks NFFTB200_CLUSTERED; Python: NfftPlan(clustered=True)): which
+    //   tiles are heavy is not known on the host, so it is decided on the device.  The hint only enables the
+    //   machinery -- it costs a uniform set ~1.5 % (measured, profiles/r02r_ab.txt), which is why it is not the
+    //   default.  The keys carry the 2 x 2 x 2 hierarchy, laid out so
     //   that the lowest radix pass covers fine bits only; that pass runs only when a sample of the keys finds a
     //   clustered set (sort.cuh: sort_points), and the work items of heavy tiles (>= dense_tile_pts points) are
     //   then marked for the 2 x 2 x 2 sweep: launch_window starts both sweeps, each takes its class of tiles.
@@ -270,6 +276,7 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
     static const bool no_fine = getenv("NFFTB200_NO_FINE_SORT") != nullptr;
     static const bool no_dense = getenv("NFFTB200_NO_DENSE") != nullptr;
     static const bool no_mixed = getenv("NFFTB200_NO_MIXED") != nullptr;
+    static const bool env_mixed = getenv("NFFTB200_MIXED") != nullptr;  // experiments: as if every call carried the hint
     static const int env_dense_pts = getenv("NFFTB200_DENSE_TILE_PTS") ? atoi(getenv("NFFTB200_DENSE_TILE_PTS")) : 0;
     if (g.use_reg == 1) {
         const bool full_tiles = g.T[0] == 16 && g.T[1] == 16 && g.T[2] == 16;
@@ -283,7 +290,7 @@ static int make_geom(Geom& g, int d, int64_t N, int m, int64_t B, int64_t C, boo
         const int mixed_mode = g_mixed_mode.load();
         const long long mixed_min = g_mixed_min_points.load();
         if (g.sc[0] != 2 && small_kernels && !no_fine && tile_bits > 0 && n_points >= mixed_min &&
-            (mixed_mode == 1 || (mixed_mode < 0 && !no_mixed && !no_dense))) {
+            (mixed_mode == 1 || (mixed_mode < 0 && (clustered_hint || env_mixed) && !no_mixed && !no_dense))) {
             const int total = 9;  // 2 x 2 x 2 supercells in a 16^3 tile: 3 (y, x) levels + 3 z bits
             const int fb = spare >= total ? total : spare + 8;
             if (tile_bits + fb <= 31) {
@@ -911,7 +918,7 @@ int64_t nfftb200_launch_count(void) { return (int64_t)g_launches.load(); }
 // out[0..24] = dim,N,M,m,L, T[3], nt[3], P[3], sY,sZ, tile_elems, ncomp, pmax, spread_threads, use_reg, fine_bits, sc[3]
 int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int flags, int64_t n, int32_t* out) {
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n));
+    NF_TRY(make_geom(g, d, N, m, B, C, geom_flags(flags & NFFTB200_X_COMPLEX, flags), n));
     int v[28] = {g.dim, g.N, g.M, g.m, g.L, g.T[0], g.T[1], g.T[2], g.nt[0], g.nt[1], g.nt[2], g.P[0], g.P[1], g.P[2],
                  g.sY, g.sZ, g.tile_elems, g.ncomp, g.pmax, g.spread_threads, g.use_reg, g.fine_bits, g.sc[0], g.sc[1],
                  g.sc[2], g.mixed, g.refine_pass, g.dense_tile_pts};
@@ -928,7 +935,7 @@ int nfftb200_debug_min_resident_ctas(void) {
 
 void nfftb200_debug_mixed(int mode, int64_t min_points, int dense_tile_pts) {
     g_mixed_mode.store(mode < 0 ? -1 : (mode ? 1 : 0));
-    g_mixed_min_points.store(min_points < 0 ? (1ll << 20) : (long long)min_points);
+    g_mixed_min_points.store(min_points < 0 ? (1ll << 18) : (long long)min_points);
     g_mixed_dense_pts.store(dense_tile_pts > 0 ? dense_tile_pts : 0);
 }
 
@@ -1009,7 +1016,7 @@ static int op_layout(int op, long long n_src, long long n_tgt, int d, int64_t N,
     bool gc, ns;
     op_modes(op, flags, &gc, &ns);
     const long long np = n_src > n_tgt ? n_src : n_tgt;
-    NF_TRY(make_geom(*g, d, N, m, B, C, gc, np));
+    NF_TRY(make_geom(*g, d, N, m, B, C, geom_flags(gc, flags), np));
     const bool planned = flags & NFFTB200_PLANNED;  // the caller brings the point plan(s): no sort regions
     const bool sym = (flags & NFFTB200_SYMMETRIC) && n_src == n_tgt;
     switch (op) {
@@ -1054,7 +1061,7 @@ size_t nfftb200_workspace_bytes(int op, int64_t n_src, int64_t n_tgt, int d, int
 
 size_t nfftb200_plan_bytes(int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B, int64_t C, int flags) {
     Geom g;
-    if (make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n_geom > n ? n_geom : n) != NFFTB200_OK) return 0;
+    if (make_geom(g, d, N, m, B, C, geom_flags(flags & NFFTB200_X_COMPLEX, flags), n_geom > n ? n_geom : n) != NFFTB200_OK) return 0;
     return align_up(plan_layout(n, g).total) + 256;
 }
 
@@ -1089,7 +1096,7 @@ int nfftb200_plan_points(const float* pos, const int64_t* batch, void* plan, siz
                          size_t workspace_bytes, void* stream) {
     NF_REQUIRE(n >= 0 && plan && workspace && (n == 0 || pos), "nfftb200_plan_points: null pointer");
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n_geom > n ? n_geom : n));
+    NF_TRY(make_geom(g, d, N, m, B, C, geom_flags(flags & NFFTB200_X_COMPLEX, flags), n_geom > n ? n_geom : n));
     if (plan_bytes < align_up(plan_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "plan buffer too small");
     if (workspace_bytes < align_up(sort_layout(n, g).total) + 256) NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small");
     SortPlan sp{};
@@ -1103,7 +1110,7 @@ int nfftb200_plan_flags(const void* plan, int64_t n, int64_t n_geom, int d, int6
                         int flags, uint32_t* flags_out, void* stream) {
     NF_REQUIRE(plan && flags_out, "nfftb200_plan_flags: null pointer");
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, n_geom > n ? n_geom : n));
+    NF_TRY(make_geom(g, d, N, m, B, C, geom_flags(flags & NFFTB200_X_COMPLEX, flags), n_geom > n ? n_geom : n));
     SortPlan sp{};
     sort_plan_pointers(n, g, align_ptr(plan), &sp);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1251,7 +1258,7 @@ int nfftb200_adjoint_finish(void* grid, void* y, int d, int64_t N, int m, int64_
     NF_REQUIRE(grid && y && workspace, "nfftb200_adjoint_finish: null pointer");
     const bool xc = flags & NFFTB200_X_COMPLEX;
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, xc, 0));
+    NF_TRY(make_geom(g, d, N, m, B, C, geom_flags(xc, 0), 0));
     float2* spec;
     FftWork fw;
     NF_TRY(spectral_layout(g, workspace, workspace_bytes, &spec, &fw));
@@ -1263,7 +1270,7 @@ int nfftb200_forward_begin(const void* xhat, void* grid, int d, int64_t N, int m
     NF_REQUIRE(xhat && grid && workspace, "nfftb200_forward_begin: null pointer");
     const bool yr = flags & NFFTB200_Y_REAL;
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, !yr, 0));
+    NF_TRY(make_geom(g, d, N, m, B, C, geom_flags(!yr, 0), 0));
     float2* spec;
     FftWork fw;
     NF_TRY(spectral_layout(g, workspace, workspace_bytes, &spec, &fw));
@@ -1275,7 +1282,7 @@ int nfftb200_fastsum_middle(void* grid, const void* coeffs, int d, int64_t N, in
                             void* workspace, size_t workspace_bytes, void* stream) {
     NF_REQUIRE(grid && coeffs && workspace, "nfftb200_fastsum_middle: null pointer");
     Geom g;
-    NF_TRY(make_geom(g, d, N, m, B, C, flags & NFFTB200_X_COMPLEX, 0));
+    NF_TRY(make_geom(g, d, N, m, B, C, geom_flags(flags & NFFTB200_X_COMPLEX, 0), 0));
     float2* spec;
     FftWork fw;
     NF_TRY(spectral_layout(g, workspace, workspace_bytes, &spec, &fw));

@@ -78,7 +78,7 @@ class CudaEngine:
             pbuf = None
             if plan is not None and n > 0:
                 pbuf = plan._sorted(N, m, C, flags)
-                flags |= _lib.PLANNED
+                flags |= plan.op_flags
             ws = _nfft._workspace(L.nfftb200_workspace_bytes(_lib.OP_SPREAD, n, 0, d, N, m, B, C, flags), pos.device)
             _lib.check(L.nfftb200_spread(pos.data_ptr(), x.data_ptr(), _nfft._ptr(batch), _nfft._ptr(pbuf),
                                          0 if pbuf is None else pbuf.numel(), grid.data_ptr(), n, d, N, m, B, C, flags,
@@ -123,7 +123,7 @@ class CudaEngine:
             pbuf = None
             if plan is not None:
                 pbuf = plan._sorted(N, m, C, flags)
-                flags |= _lib.PLANNED
+                flags |= plan.op_flags
             ws = _nfft._workspace(L.nfftb200_workspace_bytes(_lib.OP_GATHER, 0, n, d, N, m, B, C, flags), grid.device)
             _lib.check(L.nfftb200_gather(pos.data_ptr(), _nfft._ptr(batch), _nfft._ptr(pbuf),
                                          0 if pbuf is None else pbuf.numel(), grid.data_ptr(), y.data_ptr(), n, d, N, m, B,

@@ -138,21 +138,34 @@ class NfftPlan:
     `dropped_points()` reads that counter (it synchronises).
 
     `GramMatrix`, `AdjacencyMatrix` and the backward passes of the three autograd functions use plans, so
-    `A @ x` in an iterative solver bins the points once."""
+    `A @ x` in an iterative solver bins the points once.
 
-    def __init__(self, pos, batch=None, *, batch_size=None, batch_ptr=None):
+    `clustered=True` is a hint for large 3D point sets (cutoff 3 or 4) that are far from uniform: the binning
+    then samples the points on the device and, if it finds heavy grid tiles, orders their points more finely
+    and marks them for the sweep made for dense tiles (2 x 2 x 2-cell supercells).  Results are the same; a
+    Gaussian-clustered c4 runs 5 % faster with it, a uniform one 1.5 % slower (`flags()["clustered"]` tells
+    what the device found)."""
+
+    def __init__(self, pos, batch=None, *, batch_size=None, batch_ptr=None, clustered=False):
         self.pos, self.batch, self.n, self.d, self.batch_size, self.offsets = _check_points(pos, batch, batch_size, batch_ptr)
         self.device = self.pos.device
+        self.clustered = bool(clustered)
         self._sorts = {}
+
+    @property
+    def op_flags(self):
+        """Flag bits every C-ABI call that uses this plan must carry (they are part of the tiling)."""
+        return _lib.PLANNED | (_lib.CLUSTERED if self.clustered else 0)
 
     def _sorted(self, N, m, C, cplx_flag, n_geom=0):
         """(plan buffer, flags to add) for the tiling of a transform with these parameters."""
         L = _lib.lib()
-        geo = _lib.geometry(self.d, N, m, self.batch_size, C, cplx_flag, max(self.n, n_geom))
+        hint = _lib.CLUSTERED if self.clustered else 0
+        geo = _lib.geometry(self.d, N, m, self.batch_size, C, cplx_flag | hint, max(self.n, n_geom))
         key = tuple(geo[f] for f in _TILING_FIELDS)
         entry = self._sorts.get(key)
         if entry is None:
-            flags = cplx_flag | (_lib.BATCH_OFFSETS if self.offsets else 0)
+            flags = cplx_flag | hint | (_lib.BATCH_OFFSETS if self.offsets else 0)
             args = (self.n, n_geom, self.d, N, m, self.batch_size, C, flags)
             nbytes = L.nfftb200_plan_bytes(*args)
             _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
@@ -245,7 +258,7 @@ def _op_adjoint(pos, x, batch, N, m, real_output, batch_size=None, plan=None, ba
         pbuf = None
         if plan is not None:
             pbuf = plan._sorted(N, m, C, cplx)
-            flags |= _lib.PLANNED
+            flags |= plan.op_flags
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_ADJOINT, n, 0, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, pos.device)
@@ -281,7 +294,7 @@ def _op_forward(pos, xhat, batch, m, real_output, batch_size=None, plan=None, ba
         if plan is not None:
             # the gather grid is complex unless real_output: same tiling rule as a complex adjoint
             pbuf = plan._sorted(N, m, C, 0 if real_output else _lib.X_COMPLEX)
-            flags |= _lib.PLANNED
+            flags |= plan.op_flags
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_FORWARD, 0, n, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, pos.device)
@@ -331,7 +344,9 @@ def _op_fastsum(sources, targets, x, coeffs, source_batch, target_batch, m, batc
             n_geom = max(n_src, n_tgt)
             sbuf = source_plan._sorted(N, m, C, cplx, n_geom)
             tbuf = sbuf if symmetric else target_plan._sorted(N, m, C, cplx, n_geom)
-            flags |= _lib.PLANNED
+            _check(symmetric or source_plan.clustered == target_plan.clustered,
+                   "source_plan and target_plan must agree on the clustered hint")
+            flags |= source_plan.op_flags
         nbytes = L.nfftb200_workspace_bytes(_lib.OP_FASTSUM, n_src, n_tgt, d, N, m, B, C, flags)
         _check(nbytes > 0, "invalid arguments: " + L.nfftb200_last_error().decode())
         ws = _workspace(nbytes, x.device)
