@@ -33,16 +33,6 @@ struct Reg2Cfg {
     static constexpr int XYP = W + 1 + ((W + 1) % 2 == 0);  // odd window pitch, entry XYP-1 always zero
     static constexpr int WIN_FLOATS = (2 * kReg2Group * XYP + 3) / 4 * 4;
     // point record in shared memory (floats): spread [x_0..x_{NCOMP-1}, px, py, pad], gather [idx, px, py, pad]
-    // Row skipping in the gather (see RegCfg::ROWSKIP in window_reg.cuh): with W = 13 the position group 0 holds rows
-    // 0-2 and the last group row 12, and a point whose y offset in its supercell is oy has taps in rows
-    // [oy, oy + LC) only -- exactly one of the two groups is all zero for every point.
-    static constexpr int ROW_FIRST_MAX = 31 / W;
-    static constexpr int ROW_LAST_MIN = (32 * (CPL - 1)) / W;
-#ifndef NFFT_REG2_ROWSKIP
-#define NFFT_REG2_ROWSKIP 1
-#endif
-    static constexpr bool ROWSKIP = NFFT_REG2_ROWSKIP && CPL > 2 && ROW_FIRST_MAX + 1 == ROW_LAST_MIN - LC + 1 &&
-                                    ROW_FIRST_MAX + 1 == kReg2S - 1;
     static constexpr int PITCH_SPREAD = NCOMP >= 4 ? NCOMP + 4 : 4;
     static constexpr int POS_SPREAD = NCOMP == 1 ? 1 : NCOMP;
 };
@@ -125,11 +115,9 @@ __device__ __forceinline__ void bucket_points_2d(const Geom& g, const WindowArgs
 }
 
 // taps of up to kReg2Group points: lane <-> (point, dimension), L unrolled expf chains per lane
-// Returns the row-skip mask of the round (Reg2Cfg::ROWSKIP): bit 2 p + 1 set <=> the FIRST position group of point
-// p is all zero (else the last one is); 0 for configurations without row skipping.
 template <typename Cfg, int LC, int PITCH, int POS>
-__device__ __forceinline__ unsigned stage_windows_2d(const Geom& g, const float* s_rec, const unsigned char* s_off, int base,
-                                                     int npts, float* win, int lane, bool pow2) {
+__device__ __forceinline__ void stage_windows_2d(const Geom& g, const float* s_rec, const unsigned char* s_off, int base,
+                                                 int npts, float* win, int lane, bool pow2) {
     constexpr int kQuads = Cfg::WIN_FLOATS / 4;
 #pragma unroll
     for (int k = 0; k < (kQuads + 31) / 32; ++k) {
@@ -138,11 +126,9 @@ __device__ __forceinline__ unsigned stage_windows_2d(const Geom& g, const float*
     }
     __syncwarp();
     const int pt = lane >> 1, slot = lane & 1;  // slot 0 = X (API dim 1), slot 1 = Y (API dim 0)
-    bool skip_first = false;
     if (pt < npts) {
         const float p = s_rec[(size_t)(base + pt) * PITCH + POS + slot];
         const int off = (s_off[base + pt] >> (2 * slot)) & 3;
-        skip_first = slot == 1 && off > Cfg::ROW_FIRST_MAX;
         float* dst = win + (2 * pt + slot) * Cfg::XYP + off;
         const float pm = p * (float)g.M;
         const float fl = floorf(pm);  // reference cell (spatial_window_operations.cu:50)
@@ -167,7 +153,6 @@ __device__ __forceinline__ unsigned stage_windows_2d(const Geom& g, const float*
         }
     }
     __syncwarp();
-    return Cfg::ROWSKIP ? __ballot_sync(0xffffffffu, skip_first) : 0u;
 }
 
 // ======================================================================================
@@ -439,7 +424,7 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
 
         for (int base = lo; base < hi; base += kReg2Group) {
             const int npts = hi - base < kReg2Group ? hi - base : kReg2Group;
-            const unsigned skipmask = stage_windows_2d<Cfg, LC, PITCH, POS>(g, s_rec, s_off, base, npts, win, lane, pow2);
+            stage_windows_2d<Cfg, LC, PITCH, POS>(g, s_rec, s_off, base, npts, win, lane, pow2);
             const float* wv0 = win;
 #pragma unroll
             for (int gp = 0; gp < kReg2Group; ++gp) {
@@ -449,34 +434,20 @@ gather_reg2d_kernel(const Geom g, const WindowArgs a) {
                 float2 part2[NC2];
 #pragma unroll
                 for (int c = 0; c < NC2; ++c) part2[c] = make_float2(0.f, 0.f);
-                // position groups [Q0, Q1) of this point; REV: descending (keeps ptxas from merging the two row-skip
-                // variants back into one body with a predicated group, see window_reg.cuh)
-                auto groups = [&](auto q0c, auto q1c, auto revc) {
-                    constexpr int Q0 = decltype(q0c)::value, Q1 = decltype(q1c)::value;
-                    constexpr bool REV = decltype(revc)::value != 0;
 #pragma unroll
-                    for (int i = Q0; i < Q1; ++i) {
-                        const int q = REV ? Q1 - 1 - (i - Q0) : i;
-                        const float v = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X); zero for unused positions
-                        const float2 vv = make_float2(v, v);
+                for (int q = 0; q < CPL; ++q) {
+                    const float v = wv[wj[q]] * wv[wi[q]];  // psi(Y) * psi(X); zero for unused positions
+                    const float2 vv = make_float2(v, v);
 #pragma unroll
-                        for (int c = 0; c < NC2; ++c) {
-                            const float2 b2 = make_float2(blk[q][2 * c], 2 * c + 1 < NCOMP ? blk[q][2 * c + 1] : 0.f);
-                            if (NCOMP >= 2 && NFFT_REG2_FFMA2) {
-                                part2[c] = __ffma2_rn(vv, b2, part2[c]);
-                            } else {
-                                part2[c].x = fmaf(v, b2.x, part2[c].x);
-                                part2[c].y = fmaf(v, b2.y, part2[c].y);
-                            }
+                    for (int c = 0; c < NC2; ++c) {
+                        const float2 b2 = make_float2(blk[q][2 * c], 2 * c + 1 < NCOMP ? blk[q][2 * c + 1] : 0.f);
+                        if (NCOMP >= 2 && NFFT_REG2_FFMA2) {
+                            part2[c] = __ffma2_rn(vv, b2, part2[c]);
+                        } else {
+                            part2[c].x = fmaf(v, b2.x, part2[c].x);
+                            part2[c].y = fmaf(v, b2.y, part2[c].y);
                         }
                     }
-                };
-                if constexpr (Cfg::ROWSKIP) {
-                    // warp-uniform (a ballot): set = the first group of this point is all zero, else the last
-                    if (skipmask & (1u << (2 * gp + 1))) groups(IntC<1>{}, IntC<CPL>{}, IntC<1>{});
-                    else groups(IntC<0>{}, IntC<CPL - 1>{}, IntC<0>{});
-                } else {
-                    groups(IntC<0>{}, IntC<CPL>{}, IntC<0>{});
                 }
                 float part[NCOMP];
 #pragma unroll
