@@ -3,6 +3,9 @@
 R=${1:-r02u}
 mkdir -p gpurun_out
 : > gpurun_out/${R}_ab.txt
+last=$(ls gpurun_variants/lib_*.so | tail -1)
+NFFTB200_LIB=$PWD/$last timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q 2>&1 | tail -3 | tee -a gpurun_out/${R}_ab.txt
+grep -q " passed" gpurun_out/${R}_ab.txt && ! grep -q "failed" gpurun_out/${R}_ab.txt || { echo "tests failed: no A/B"; exit 0; }
 for rep in 1 2; do
 for WL in c4 c4_clustered; do
 for f in gpurun_variants/lib_*.so; do

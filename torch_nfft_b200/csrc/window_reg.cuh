@@ -456,7 +456,7 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
             // than index shared memory out of bounds, and count it in the plan's flag word
             if (cx >= 0 && cy >= 0 && cz >= 0 && bx < nsx && by < nsy && bz < nsz) {
                 const int zf = ZR > 0 ? cz % ZR : cz - bz * SZ;
-                sc[k] = ((by * nsx + bx) * nsz + bz) | ((cx - bx * SX) | (cy - by * SY) << 2 | zf << 4) << 24;
+                sc[k] = ((by * nsx + bx) * nsz + bz) | (int)((unsigned)((cx - bx * SX) | (cy - by * SY) << 2 | zf << 4) << 24);
                 atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
             } else {
                 note_dropped_point(a);
@@ -486,7 +486,7 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-        if (sc[k] >= 0) {
+        if (sc[k] != -1) {  // (not ">= 0": a 4-bit z field reaches bit 31)
             const int dst = atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
             s_pts[dst] = pt[k];
             s_off[dst] = (unsigned char)((unsigned)sc[k] >> 24);
