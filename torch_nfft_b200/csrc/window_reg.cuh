@@ -422,9 +422,7 @@ inline size_t reg_smem_bytes(const Geom& g, int nsc, int win_floats) {
 // Loads the chunk's points, buckets them by supercell (column-major: z fastest) and leaves them in
 // s_pts as (pos0, pos1, pos2, w), w = x value (spread) or original index (gather), together with
 // the cell offsets inside the supercell s_off = ox | oy << 2 | oz << 4.
-// ZR > 0 (rotating z block of the gather, see gather_reg_body): the z field of s_off is 4 bits wide and holds the
-// point's tile-local z cell modulo ZR = the position of its first tap in the circular z window.
-template <int SX, int SY, int SZ, bool SPREAD, int ZR = 0>
+template <int SX, int SY, int SZ, bool SPREAD>
 __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a, const TileCtx& t, int cnt,
                                               int nsx, int nsy, int nsz, float4* s_pts, unsigned char* s_off,
                                               int* s_start, int* s_cur) {
@@ -455,8 +453,7 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
             // a point outside its tile can only come from a stale / foreign plan: drop it rather
             // than index shared memory out of bounds, and count it in the plan's flag word
             if (cx >= 0 && cy >= 0 && cz >= 0 && bx < nsx && by < nsy && bz < nsz) {
-                const int zf = ZR > 0 ? cz % ZR : cz - bz * SZ;
-                sc[k] = ((by * nsx + bx) * nsz + bz) | (int)((unsigned)((cx - bx * SX) | (cy - by * SY) << 2 | zf << 4) << 24);
+                sc[k] = ((by * nsx + bx) * nsz + bz) | ((cx - bx * SX) | (cy - by * SY) << 2 | (cz - bz * SZ) << 4) << 24;
                 atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
             } else {
                 note_dropped_point(a);
@@ -486,7 +483,7 @@ __device__ __forceinline__ void bucket_points(const Geom& g, const WindowArgs& a
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-        if (sc[k] != -1) {  // (not ">= 0": a 4-bit z field reaches bit 31)
+        if (sc[k] >= 0) {
             const int dst = atomicAdd(&s_cur[sc[k] & 0xffffff], 1);
             s_pts[dst] = pt[k];
             s_off[dst] = (unsigned char)((unsigned)sc[k] >> 24);
@@ -679,19 +676,13 @@ __device__ __forceinline__ unsigned stage_windows(const Geom& g, uint32_t pts_sh
     return Cfg::ROWSKIP ? __ballot_sync(0xffffffffu, skip_first) : 0u;
 }
 
-#ifndef NFFT_REG_ROTZ
-#define NFFT_REG_ROTZ 1  // gather: rotating z block instead of the slide (gather_reg_body)
-#endif
 // The tap staging through generic pointers is the default: the variant above (opaque shared addresses, 22 fewer
 // instructions per round) measured SLOWER on the B200 (c4: spread 4.08 vs 4.04 ms, gather 3.35 vs 3.29 ms,
 // profiles/r02d_ab.txt) -- its volatile accesses pin the order of the loads and stores of a round.
 #ifndef NFFT_REG_OLD_STAGE
 #define NFFT_REG_OLD_STAGE 1
 #endif
-// ROTZ (gather): the z window is CIRCULAR with period 2 ZP -- tap l of a point whose tile-local z cell is cz goes
-// to entry (cz + l) mod 2 ZP, so that entry pair kp always weights the tile plane pair P with P mod ZP == kp and the
-// register block never has to slide (gather_reg_body).
-template <typename Cfg, int LC, bool SCALE_Z = false, bool ROTZ = false>
+template <typename Cfg, int LC, bool SCALE_Z = false>
 __device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const float4* s_pts, const unsigned char* s_off,
                                                           int base, int npts, float* win, int lane, bool pow2) {
     constexpr int kQuads = Cfg::WIN_FLOATS / 4;
@@ -706,10 +697,7 @@ __device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const f
     if (pt < npts) {
         const int slot = 2 - api;
         const float p = reinterpret_cast<const float*>(s_pts + base + pt)[api];
-        constexpr int ZR = 2 * Cfg::ZP;
-        const int so = s_off[base + pt];
-        const int off = ROTZ && slot == 2 ? so >> 4 : (so >> (2 * slot)) & 3;
-        const int wrapl = ROTZ && slot == 2 ? ZR - off : LC;  // taps l >= wrapl continue at the start of the window
+        const int off = (s_off[base + pt] >> (2 * slot)) & 3;
         constexpr int kXY = (2 * kRegGroup * Cfg::XYP + 3) / 4 * 4;
         float* dst = slot == 2 ? win + kXY + pt * Cfg::ZWP + off : win + (2 * pt + slot) * Cfg::XYP + off;
         const float pm = p * (float)g.M;
@@ -724,12 +712,12 @@ __device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const f
             // to the reference's (float)((double)pos * 2N - shift - l)
             const float frac = pm - fl;
 #if NFFT_WINDOW_RECUR
-            window_taps_recur<LC>(g, frac, amp, [&](int l, float v) { dst[ROTZ && l >= wrapl ? l - ZR : l] = v; });
+            window_taps_recur<LC>(g, frac, amp, [&](int l, float v) { dst[l] = v; });
 #else
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = frac + (float)((LC - 2) / 2 - l);  // m - l, m = (L - 2) / 2
-                dst[ROTZ && l >= wrapl ? l - ZR : l] = window_exp(-(tt * tt) * g.inv_b) * amp;  // eval_phi, :24-28
+                dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;  // eval_phi, :24-28
             }
 #endif
         } else {
@@ -737,7 +725,7 @@ __device__ __forceinline__ unsigned stage_windows_generic(const Geom& g, const f
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 const float tt = (float)(bd - (double)l);
-                dst[ROTZ && l >= wrapl ? l - ZR : l] = window_exp(-(tt * tt) * g.inv_b) * amp;
+                dst[l] = window_exp(-(tt * tt) * g.inv_b) * amp;
             }
         }
     }
@@ -1051,12 +1039,6 @@ __device__ __forceinline__ void gather_reg_body(const Geom& g, const WindowArgs&
                                                 const TileCtx& t) {
     using Cfg = RegCfg<LC, SX, SY, SZ>;
     constexpr int WX = Cfg::WX, WZ = Cfg::WZ, CPL = Cfg::CPL, ZP = Cfg::ZP, SP = SZ / 2;
-    // Rotating z block: register pair r of the block always holds the tile plane pair P with P mod ZP == r, and the
-    // z taps are staged into a circular window to match (stage_windows_generic<.., ROTZ>).  When the sweep moves up
-    // one supercell only the pair that left the block is reloaded, into the register it vacated (a switch over the
-    // ZP registers) -- instead of sliding all CPL * (ZP - 1) pairs down by one (84 of the 110 instructions of an
-    // advance at L = 10).
-    constexpr bool kRotZ = NFFT_REG_ROTZ && SP == 1 && NFFT_REG_OLD_STAGE;
     extern __shared__ __align__(128) float smem_reg[];
     NFFT_PHASE_MARK(ph0);
     NFFT_PHASE_BEGIN(1);
@@ -1117,7 +1099,7 @@ __device__ __forceinline__ void gather_reg_body(const Geom& g, const WindowArgs&
     __syncthreads();
     NFFT_PHASE_MARK(pha);
     const int cnt = (int)(t.p_hi - t.p_lo);
-    bucket_points<SX, SY, SZ, false, kRotZ ? 2 * ZP : 0>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
+    bucket_points<SX, SY, SZ, false>(g, a, t, cnt, nsx, nsy, nsz, s_pts, s_off, s_start, s_cur);
     NFFT_PHASE_MARK(phb);
     if (tma_tile) {
         // every thread observes the completion itself (the mbarrier makes the TMA writes visible to its waiters)
@@ -1194,60 +1176,21 @@ __device__ __forceinline__ void gather_reg_body(const Geom& g, const WindowArgs&
 #pragma unroll
             for (int q = 0; q < CPL; ++q) blk[q][kp] = make_float2(lds_at(aq[q] + oa), lds_at(aq[q] + ob));
         };
-        // kRotZ: plane pair `pair` (planes 2 pair, 2 pair + 1 of the column, clamped) into register pair R
-        auto load_abs = [&](auto rc, int pair) {
-            constexpr int R = decltype(rc)::value;
-            const int z0 = 2 * pair;
-            const uint32_t oa = (uint32_t)(z0 < zmax ? z0 : zmax) * sz4, ob = (uint32_t)(z0 + 1 < zmax ? z0 + 1 : zmax) * sz4;
 #pragma unroll
-            for (int q = 0; q < CPL; ++q) blk[q][R] = make_float2(lds_at(aq[q] + oa), lds_at(aq[q] + ob));
-        };
-        int rcur = 0;  // kRotZ: the register pair that holds the block's bottom plane pair (= scz mod ZP)
-        if constexpr (kRotZ) {
-            rcur = scz % ZP;
-            // register r holds the pair P in [scz, scz + ZP) with P mod ZP == r
-            auto init = [&](auto rc) {
-                constexpr int R = decltype(rc)::value;
-                load_abs(rc, scz + (R >= rcur ? R - rcur : R - rcur + ZP));
-            };
-            init(IntC<0>{});
-            if constexpr (ZP > 1) init(IntC<1>{});
-            if constexpr (ZP > 2) init(IntC<2>{});
-            if constexpr (ZP > 3) init(IntC<3>{});
-            if constexpr (ZP > 4) init(IntC<4>{});
-            if constexpr (ZP > 5) init(IntC<5>{});
-            static_assert(ZP <= 6, "rotating z block: one case per register pair");
-        } else {
-#pragma unroll
-            for (int kp = 0; kp < ZP; ++kp) load_pair(kp, scz);
-        }
+        for (int kp = 0; kp < ZP; ++kp) load_pair(kp, scz);
         auto advance = [&](int scz) {
-            if constexpr (kRotZ) {
-                // the block origin moved from supercell scz - 1 to scz: pair scz - 1 left, pair scz - 1 + ZP enters
-                const int pair = scz - 1 + ZP;
-                switch (rcur) {
-                    case 0: load_abs(IntC<0>{}, pair); break;
-                    case 1: if constexpr (ZP > 1) load_abs(IntC<1>{}, pair); break;
-                    case 2: if constexpr (ZP > 2) load_abs(IntC<2>{}, pair); break;
-                    case 3: if constexpr (ZP > 3) load_abs(IntC<3>{}, pair); break;
-                    case 4: if constexpr (ZP > 4) load_abs(IntC<4>{}, pair); break;
-                    default: if constexpr (ZP > 5) load_abs(IntC<5>{}, pair); break;
-                }
-                rcur = rcur + 1 == ZP ? 0 : rcur + 1;
-            } else {
 #pragma unroll
-                for (int kp = 0; kp + SP < ZP; ++kp)
+            for (int kp = 0; kp + SP < ZP; ++kp)
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) blk[q][kp] = blk[q][kp + SP];
+                for (int q = 0; q < CPL; ++q) blk[q][kp] = blk[q][kp + SP];
 #pragma unroll
-                for (int kp = ZP - SP; kp < ZP; ++kp) load_pair(kp, scz);
-            }
+            for (int kp = ZP - SP; kp < ZP; ++kp) load_pair(kp, scz);
         };
 
         for (int base = lo_col; base < hi_col; base += kRegGroup) {
             const int npts = hi_col - base < kRegGroup ? hi_col - base : kRegGroup;
 #if NFFT_REG_OLD_STAGE
-            const unsigned skipmask = stage_windows_generic<Cfg, LC, false, kRotZ>(g, s_pts, s_off, base, npts, win, lane, pow2);
+            const unsigned skipmask = stage_windows_generic<Cfg, LC>(g, s_pts, s_off, base, npts, win, lane, pow2);
 #else
             const unsigned skipmask = stage_windows<Cfg, LC>(g, pts_sh, base, npts, wbase, lane, pow2);
 #endif
