@@ -190,6 +190,10 @@ int nfftb200_profile_read(double* ms_out, int64_t* count_out);
 /* Tests: force the 64-bit index variants of the spectral kernels (normally chosen when B*C*M^d >= 2^31). */
 void nfftb200_debug_force_int64(int on);
 
+/* Tests / experiments: the pruned real transforms (hand-written X pass + cuFFT C2C over the kept kx planes; grids
+ * with 256 or 512 cells per dimension, d = 2, 3).  mode -1 = default (on), 0 = plain cuFFT R2C / C2R, 1 = on. */
+void nfftb200_debug_pruned_fft(int mode);
+
 /* Tests: the smallest number of resident CTAs per SM the runtime reported for any launch configuration of the 3D
  * register-stencil sweeps so far (they are built for 2; -1 = none launched yet). */
 int nfftb200_debug_min_resident_ctas(void);

@@ -657,3 +657,33 @@ def test_mixed_density_binning_is_bit_exact(mixed_mode):
         assert np.array_equal(keys.cpu().numpy().astype(np.int64), okeys)
         expect = O.stable_permutation(okeys if clustered else okeys >> 8)
         assert np.array_equal(perm.cpu().numpy().astype(np.int64), expect)
+
+
+# ---------------------------------------------------------------------------------------------
+# pruned real transforms (hand-written X pass with the crop + cuFFT C2C over the kept kx planes) against the plain
+# cuFFT R2C / C2R path of the same library
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,N,B,C", [(3, 128, 2, 1), (2, 128, 3, 2), (2, 256, 2, 1), (2, 256, 1, 8)])
+def test_pruned_fft_matches_cufft_path(d, N, B, C):
+    rng = np.random.default_rng(100 * d + N + C)
+    m, n = 4, 20000
+    pos, batch = make_points(rng, d, B, n)
+    x = make_values(rng, (pos.shape[0], C) if C > 1 else (pos.shape[0],), False)
+    spec = make_values(rng, (B,) + (N,) * d + ((C,) if C > 1 else ()), True)
+    tp, tb, tx, ts = cuda(pos), cuda(batch), cuda(x), cuda(spec)
+    L = _lib.lib()
+    out = {}
+    try:
+        for mode in (1, 0):
+            L.nfftb200_debug_pruned_fft(mode)
+            out[mode] = (T.nfft_adjoint(tx, tp, tb, N, m).cpu().numpy(),                     # real grid: R2C
+                         T.nfft_adjoint(tx, tp, tb, N, m, real_output=True).cpu().numpy(),
+                         T.nfft_forward(ts, tp, tb, m, real_output=True).cpu().numpy())      # real grid: C2R
+    finally:
+        L.nfftb200_debug_pruned_fft(-1)
+    for a, b in zip(out[1], out[0]):
+        assert a.shape == b.shape and O.rel_l2(a, b) < 2e-6, O.rel_l2(a, b)
+    # and against the oracle on the smallest of them
+    if d == 2 and N == 128 and C == 2:
+        assert O.rel_l2(out[1][0], O.nfft_adjoint(x, pos, batch, N, m)) < TOL
+        assert O.rel_l2(out[1][2], O.nfft_forward(spec, pos, batch, m, real_output=True)) < TOL

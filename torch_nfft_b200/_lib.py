@@ -30,6 +30,7 @@ _SIGNATURES = {
     "nfftb200_debug_force_int64": (None, [_i32]),
     "nfftb200_debug_mixed": (None, [_i32, _i64, _i32]),
     "nfftb200_debug_min_resident_ctas": (_i32, []),
+    "nfftb200_debug_pruned_fft": (None, [_i32]),
     # (n, n_geom, d, N, m, B, C, flags)
     "nfftb200_plan_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32, _i64, _i64, _i32]),
     # (pos, batch, plan, plan_bytes, n, n_geom, d, N, m, B, C, flags, ws, ws_bytes, stream)

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "sort.cuh"
 #include "spectral.cuh"
+#include "fft_rows.cuh"
 #include "window.cuh"
 #include "window_reg.cuh"
 #include "window_reg2d.cuh"
@@ -649,6 +650,18 @@ static int get_plan_locked(int dim, int M, long long batch, cufftType type, Plan
 
 // bytes of cuFFT work area the transforms of one op need (the maximum over the plans it runs); 0 when no
 // device is usable (host-only size queries): the op itself then fails with a clear message
+// Pruned real transforms (fft_rows.cuh): hand-written X pass + cuFFT C2C over the other d - 1 dimensions of the
+// kept kx planes.  -1 = default (on unless NFFTB200_NO_PRUNED_FFT is set), 0 = off, 1 = on; test hook
+// nfftb200_debug_pruned_fft.  The fastsum keeps the plain R2C / C2R pair (its spectrum is not cropped in between).
+static std::atomic<int> g_pruned_mode{-1};
+static bool pruned_fft_ok(const Geom& g) {
+    static const bool env_off = getenv("NFFTB200_NO_PRUNED_FFT") != nullptr;
+    const int mode = g_pruned_mode.load();
+    if (mode == 0 || (mode < 0 && env_off)) return false;
+    return (g.dim == 2 || g.dim == 3) && (g.M == 256 || g.M == 512) && g.N == g.M / 2;
+}
+static long long pruned_batch(const Geom& g) { return (long long)g.B * g.C * (g.N / 2 + 1); }
+
 static size_t fft_work_bytes(const Geom& g, bool grid_cplx) {
     std::lock_guard<std::mutex> lock(g_plan_mutex);
     size_t need = 0;
@@ -659,6 +672,9 @@ static size_t fft_work_bytes(const Geom& g, bool grid_cplx) {
     } else {
         if (get_plan_locked(g.dim, g.M, batch, CUFFT_R2C, &e) == NFFTB200_OK) need = e->work;
         if (get_plan_locked(g.dim, g.M, batch, CUFFT_C2R, &e) == NFFTB200_OK && e->work > need) need = e->work;
+        if (pruned_fft_ok(g) && get_plan_locked(g.dim - 1, g.M, pruned_batch(g), CUFFT_C2C, &e) == NFFTB200_OK &&
+            e->work > need)
+            need = e->work;
     }
     (void)cudaGetLastError();
     if (e == nullptr) g_err[0] = 0;  // no usable device: not an error of a size query
@@ -672,12 +688,14 @@ struct FftWork {
 
 enum FftKind { FFT_R2C, FFT_C2R, FFT_C2C_INVERSE, FFT_C2C_FORWARD };
 
-// one transform of all B*C grids on the caller's stream with the caller's work area
-static int fft_exec(const Geom& g, FftKind kind, void* in, void* out, const FftWork& work, cudaStream_t st) {
+// one batched transform (dim dimensions of M cells, `batch` contiguous arrays) on the caller's stream with the
+// caller's work area
+static int fft_exec_dims(int dim, int M, long long batch, FftKind kind, void* in, void* out, const FftWork& work,
+                         cudaStream_t st) {
     const cufftType type = kind == FFT_R2C ? CUFFT_R2C : (kind == FFT_C2R ? CUFFT_C2R : CUFFT_C2C);
     std::lock_guard<std::mutex> lock(g_plan_mutex);
     PlanEntry* e = nullptr;
-    NF_TRY(get_plan_locked(g.dim, g.M, (long long)g.B * g.C, type, &e));
+    NF_TRY(get_plan_locked(dim, M, batch, type, &e));
     if (e->work > work.bytes)
         NF_FAIL(NFFTB200_ERR_WORKSPACE, "workspace too small for the cuFFT work area: %zu < %zu", work.bytes, e->work);
     NF_CUFFT(cufftSetStream(e->handle, st));
@@ -694,6 +712,10 @@ static int fft_exec(const Geom& g, FftKind kind, void* in, void* out, const FftW
             break;
     }
     return NFFTB200_OK;
+}
+// one transform of all B*C grids
+static int fft_exec(const Geom& g, FftKind kind, void* in, void* out, const FftWork& work, cudaStream_t st) {
+    return fft_exec_dims(g.dim, g.M, (long long)g.B * g.C, kind, in, out, work, st);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -750,11 +772,15 @@ static int do_sort(const Geom& g, const float* pos, const int64_t* batch, bool o
 
 // spectral kernels use 32-bit index arithmetic whenever every element index fits 31 bits
 template <int DIM, typename I>
-static int launch_unpack_t(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st) {
+static int launch_unpack_t(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st,
+                           bool pruned) {
     long long total = (long long)g.B * g.C;
     for (int a = 0; a < DIM; ++a) total *= g.N;
     const unsigned grid = blocks_for(total);
-    if (half) {
+    if (half && pruned) {
+        if (real_out) NF_LAUNCH((unpack_kernel<DIM, true, true, I, true>), grid, 256, 0, st, spec, y, g);
+        else NF_LAUNCH((unpack_kernel<DIM, true, false, I, true>), grid, 256, 0, st, spec, y, g);
+    } else if (half) {
         if (real_out) NF_LAUNCH((unpack_kernel<DIM, true, true, I>), grid, 256, 0, st, spec, y, g);
         else NF_LAUNCH((unpack_kernel<DIM, true, false, I>), grid, 256, 0, st, spec, y, g);
     } else {
@@ -765,14 +791,19 @@ static int launch_unpack_t(const Geom& g, bool half, bool real_out, const float2
 }
 
 template <int DIM, typename I>
-static int launch_pack_t(const Geom& g, bool half, bool xreal, const float* xhat, float2* spec, cudaStream_t st) {
+static int launch_pack_t(const Geom& g, bool half, bool xreal, const float* xhat, float2* spec, cudaStream_t st,
+                         bool pruned) {
     // zero fill (out-of-band 7/8 of a 3D spectrum) with one memset, then write the band box
-    const long long total = half ? half_elems(g) : (long long)g.B * g.C * g.Md;
+    long long total = half ? half_elems(g) : (long long)g.B * g.C * g.Md;
+    if (half && pruned) total = pruned_batch(g) * (g.Md / g.M);  // P[bc][kx][M^(d-1)]
     NF_CUDA(cudaMemsetAsync(spec, 0, (size_t)total * sizeof(float2), st));
     long long band = (long long)g.B * g.C * (half ? g.N / 2 + 1 : g.N);
     for (int a = 0; a < DIM - 1; ++a) band *= half ? g.N + 1 : g.N;
     const unsigned grid = blocks_for(band);
-    if (half) {
+    if (half && pruned) {
+        if (xreal) NF_LAUNCH((pack_kernel<DIM, true, true, I, true>), grid, 256, 0, st, xhat, spec, g);
+        else NF_LAUNCH((pack_kernel<DIM, true, false, I, true>), grid, 256, 0, st, xhat, spec, g);
+    } else if (half) {
         if (xreal) NF_LAUNCH((pack_kernel<DIM, true, true, I>), grid, 256, 0, st, xhat, spec, g);
         else NF_LAUNCH((pack_kernel<DIM, true, false, I>), grid, 256, 0, st, xhat, spec, g);
     } else {
@@ -805,14 +836,43 @@ static bool fits_int32(const Geom& g) {
     return (long long)g.B * g.C * g.Md < (1ll << 31) - 1024;
 }
 template <int DIM>
-static int launch_unpack(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st) {
-    return fits_int32(g) ? launch_unpack_t<DIM, int>(g, half, real_out, spec, y, st)
-                         : launch_unpack_t<DIM, long long>(g, half, real_out, spec, y, st);
+static int launch_unpack(const Geom& g, bool half, bool real_out, const float2* spec, float* y, cudaStream_t st,
+                         bool pruned = false) {
+    return fits_int32(g) ? launch_unpack_t<DIM, int>(g, half, real_out, spec, y, st, pruned)
+                         : launch_unpack_t<DIM, long long>(g, half, real_out, spec, y, st, pruned);
 }
 template <int DIM>
-static int launch_pack(const Geom& g, bool half, bool xreal, const float* xhat, float2* spec, cudaStream_t st) {
-    return fits_int32(g) ? launch_pack_t<DIM, int>(g, half, xreal, xhat, spec, st)
-                         : launch_pack_t<DIM, long long>(g, half, xreal, xhat, spec, st);
+static int launch_pack(const Geom& g, bool half, bool xreal, const float* xhat, float2* spec, cudaStream_t st,
+                       bool pruned = false) {
+    return fits_int32(g) ? launch_pack_t<DIM, int>(g, half, xreal, xhat, spec, st, pruned)
+                         : launch_pack_t<DIM, long long>(g, half, xreal, xhat, spec, st, pruned);
+}
+
+// the hand-written X pass of the pruned real transforms (fft_rows.cuh)
+static int launch_fft_rows(const Geom& g, bool forward_r2c, float* grid, float2* P, cudaStream_t st) {
+    const long long rows_per_bc = g.Md / g.M, rows = (long long)g.B * g.C * rows_per_bc;
+    const unsigned ctas = (unsigned)(rows / kFftRowsPerCta);
+    ProfScope ps(ST_FFT, st);
+    if (g.M == 256) {
+        const size_t smem = fft_rows_smem_bytes<16>();
+        if (forward_r2c) {
+            NF_TRY(ensure_dynamic_smem((const void*)rows_r2c_crop_kernel<16>, smem));
+            NF_LAUNCH(rows_r2c_crop_kernel<16>, ctas, kFftThreads, smem, st, grid, P, rows_per_bc);
+        } else {
+            NF_TRY(ensure_dynamic_smem((const void*)rows_c2r_pad_kernel<16>, smem));
+            NF_LAUNCH(rows_c2r_pad_kernel<16>, ctas, kFftThreads, smem, st, P, grid, rows_per_bc);
+        }
+    } else {
+        const size_t smem = fft_rows_smem_bytes<32>();
+        if (forward_r2c) {
+            NF_TRY(ensure_dynamic_smem((const void*)rows_r2c_crop_kernel<32>, smem));
+            NF_LAUNCH(rows_r2c_crop_kernel<32>, ctas, kFftThreads, smem, st, grid, P, rows_per_bc);
+        } else {
+            NF_TRY(ensure_dynamic_smem((const void*)rows_c2r_pad_kernel<32>, smem));
+            NF_LAUNCH(rows_c2r_pad_kernel<32>, ctas, kFftThreads, smem, st, P, grid, rows_per_bc);
+        }
+    }
+    return NFFTB200_OK;
 }
 template <int DIM>
 static int launch_multiply(const Geom& g, bool half, bool creal, float2* spec, const float* coeffs, cudaStream_t st) {
@@ -826,6 +886,14 @@ static int launch_multiply(const Geom& g, bool half, bool creal, float2* spec, c
 // grid (real: [BC][M^d] float, complex: [BC][M^d] float2) -> y.  spec: scratch for the half spectrum.
 static int do_adjoint_finish(const Geom& g, float* grid, float* y, bool real_out, float2* spec, const FftWork& fw,
                              cudaStream_t st) {
+    if (!g.cplx && pruned_fft_ok(g)) {
+        // R2C along X with the crop to kx <= N/2, then C2C (sign -) over the other dimensions of the kept planes:
+        // P[bc][kx][..] holds what the full R2C transform holds at those frequencies
+        NF_TRY(launch_fft_rows(g, true, grid, spec, st));
+        NF_TRY(fft_exec_dims(g.dim - 1, g.M, pruned_batch(g), FFT_C2C_FORWARD, spec, spec, fw, st));
+        ProfScope ps(ST_UNPACK, st);
+        return NF_DIM_DISPATCH(launch_unpack, g, true, real_out, spec, y, st, true);
+    }
     if (!g.cplx) {
         NF_TRY(fft_exec(g, FFT_R2C, grid, spec, fw, st));
         ProfScope ps(ST_UNPACK, st);
@@ -839,6 +907,16 @@ static int do_adjoint_finish(const Geom& g, float* grid, float* y, bool real_out
 // xhat -> grid.  real_out: grid is float (C2R), else float2 (C2C sign -).
 static int do_forward_begin(const Geom& g, const float* xhat, bool xreal, bool real_out, float* grid, float2* spec,
                             const FftWork& fw, cudaStream_t st) {
+    if (real_out && pruned_fft_ok(g)) {
+        // the C2R input restricted to kx <= N/2 (everything above is zero): C2C (sign +) over the other
+        // dimensions of those planes, then the C2R X pass from the kept frequencies
+        {
+            ProfScope ps(ST_PACK, st);
+            NF_TRY(NF_DIM_DISPATCH(launch_pack, g, true, xreal, xhat, spec, st, true));
+        }
+        NF_TRY(fft_exec_dims(g.dim - 1, g.M, pruned_batch(g), FFT_C2C_INVERSE, spec, spec, fw, st));
+        return launch_fft_rows(g, false, grid, spec, st);
+    }
     if (real_out) {
         {
             ProfScope ps(ST_PACK, st);
@@ -927,6 +1005,8 @@ int nfftb200_debug_geometry(int d, int64_t N, int m, int64_t B, int64_t C, int f
 }
 
 void nfftb200_debug_force_int64(int on) { g_force_int64.store(on ? 1 : 0); }
+
+void nfftb200_debug_pruned_fft(int mode) { g_pruned_mode.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
 
 int nfftb200_debug_min_resident_ctas(void) {
     const int v = g_min_resident.load();

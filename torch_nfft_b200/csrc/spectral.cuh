@@ -28,7 +28,8 @@ __device__ __forceinline__ int wrapM(int k, int M) { return k < 0 ? k + M : k; }
 //   HALF: spec is the R2C half spectrum [BC][M]..[M][M/2+1];  else full C2C (+ sign) [BC][M]^d
 // ---------------------------------------------------------------------------------------
 // I = int when every index fits 31 bits (64-bit divisions are ~10x dearer), long long otherwise
-template <int DIM, bool HALF, bool REAL_OUT, typename I>
+// PRUNED (with HALF): spec is P[BC][N/2+1][M]..[M] -- the kept kx outermost, see fft_rows.cuh
+template <int DIM, bool HALF, bool REAL_OUT, typename I, bool PRUNED = false>
 __global__ void __launch_bounds__(256)
 unpack_kernel(const float2* __restrict__ spec, float* __restrict__ y, Geom g) {
     const I total = (I)g.B * g.C;
@@ -54,9 +55,10 @@ unpack_kernel(const float2* __restrict__ spec, float* __restrict__ y, Geom g) {
         const int H = g.M / 2 + 1;
         const bool neg = k[DIM - 1] < 0;
         I s = bc;
+        if (PRUNED) s = s * (g.N / 2 + 1) + (neg ? -k[DIM - 1] : k[DIM - 1]);
 #pragma unroll
         for (int a = 0; a < DIM - 1; ++a) s = s * g.M + wrapM(neg ? -k[a] : k[a], g.M);
-        s = s * H + (neg ? -k[DIM - 1] : k[DIM - 1]);
+        if (!PRUNED) s = s * H + (neg ? -k[DIM - 1] : k[DIM - 1]);
         v = spec[s];
         if (!neg) v.y = -v.y;
     } else {
@@ -130,7 +132,7 @@ __device__ __forceinline__ float rolloff(const int kap[3], float c_hat) {
 // HALF = true : input of the C2R transform (Hermitian part, conjugated);  false: input of C2C(-).
 // The spectrum is zero outside the band, so the host zero-fills it with one memset and this kernel
 // visits only the band box: kappa_a in [-N/2, N/2] (HALF: last dim [0, N/2]) resp. [-N/2, N/2-1].
-template <int DIM, bool HALF, bool XREAL, typename I>
+template <int DIM, bool HALF, bool XREAL, typename I, bool PRUNED = false>
 __global__ void __launch_bounds__(256)
 pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
     const int ext = HALF ? g.N + 1 : g.N;            // band extent of the leading dims
@@ -153,9 +155,10 @@ pack_kernel(const float* __restrict__ xhat, float2* __restrict__ spec, Geom g) {
     const int c = (int)(bc % g.C);
     // position in the planar spectrum
     I dst = bc;
+    if (PRUNED) dst = dst * (g.N / 2 + 1) + kap[DIM - 1];  // P[bc][kx][..] (HALF only)
 #pragma unroll
     for (int a = 0; a < DIM - 1; ++a) dst = dst * g.M + wrapM(kap[a], g.M);
-    dst = dst * (HALF ? g.M / 2 + 1 : g.M) + (HALF ? kap[DIM - 1] : wrapM(kap[DIM - 1], g.M));
+    if (!PRUNED) dst = dst * (HALF ? g.M / 2 + 1 : g.M) + (HALF ? kap[DIM - 1] : wrapM(kap[DIM - 1], g.M));
 
     const bool pos_in = in_band<DIM>(kap, 1, g.N);
     float2 out = make_float2(0.f, 0.f);
