@@ -12,7 +12,7 @@ run() {
   echo "$1 $2 $v" | tee -a gpurun_out/${R}_ab.txt
 }
 for rep in 1 2; do
-for WL in c4 c3; do
+for WL in c4; do
 for E in NFFTB200_NO_PRUNED_FFT=1 X=1; do run $WL $E; done
 done
 done
