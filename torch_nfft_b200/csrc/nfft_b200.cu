@@ -660,7 +660,8 @@ static bool pruned_fft_ok(const Geom& g) {
     if (mode == 0 || (mode < 0 && env_off)) return false;
     // 3D only: in 2D the crop saves one quarter of one cuFFT pass and costs as much in the transposed accesses of
     // pack / unpack (c3: 3.817 vs 3.821 ms, profiles/r02w_ab.txt); mode 1 (tests) also takes the 2D grids
-    return (g.dim == 3 || (g.dim == 2 && mode == 1)) && (g.M == 256 || g.M == 512) && g.N == g.M / 2;
+    static const bool env_2d = getenv("NFFTB200_PRUNED_2D") != nullptr;  // experiment switch
+    return (g.dim == 3 || (g.dim == 2 && (mode == 1 || env_2d))) && (g.M == 256 || g.M == 512) && g.N == g.M / 2;
 }
 static long long pruned_batch(const Geom& g) { return (long long)g.B * g.C * (g.N / 2 + 1); }
 
