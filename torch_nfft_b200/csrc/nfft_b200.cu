@@ -658,10 +658,9 @@ static bool pruned_fft_ok(const Geom& g) {
     static const bool env_off = getenv("NFFTB200_NO_PRUNED_FFT") != nullptr;
     const int mode = g_pruned_mode.load();
     if (mode == 0 || (mode < 0 && env_off)) return false;
-    // 3D only: in 2D the crop saves one quarter of one cuFFT pass and costs as much in the transposed accesses of
-    // pack / unpack (c3: 3.817 vs 3.821 ms, profiles/r02w_ab.txt); mode 1 (tests) also takes the 2D grids
-    static const bool env_2d = getenv("NFFTB200_PRUNED_2D") != nullptr;  // experiment switch
-    return (g.dim == 3 || (g.dim == 2 && (mode == 1 || env_2d))) && (g.M == 256 || g.M == 512) && g.N == g.M / 2;
+    // (2D and 3D real transforms on 256- and 512-cell grids: c4 FFT stages 0.71 -> 0.40 ms, c3 0.29 -> 0.20 ms,
+    // profiles/r02x_ab.txt, r02y_ab.txt)
+    return (g.dim == 2 || g.dim == 3) && (g.M == 256 || g.M == 512) && g.N == g.M / 2;
 }
 static long long pruned_batch(const Geom& g) { return (long long)g.B * g.C * (g.N / 2 + 1); }
 
