@@ -204,15 +204,17 @@ __device__ __forceinline__ long long batch_of(const BatchRef& br, long long i) {
 // a z-range of it -- instead of random samples of the whole tile, so the points of a chunk share register
 // blocks in the sweep (window_reg.cuh).
 __device__ __forceinline__ uint32_t fine_index(int cx, int cy, int cz, const Geom& g) {
-    const int bx = cx / g.sc[0], by = cy / g.sc[1], bz = cz / g.sc[2];
+    // supercell extents are powers of two whenever fine bits are used (make_geom): shifts, not divisions
+    const int bx = cx >> (__ffs(g.sc[0]) - 1), by = cy >> (__ffs(g.sc[1]) - 1), bz = cz >> (__ffs(g.sc[2]) - 1);
     uint32_t f = 0;
     for (int b = g.fine_xy_levels - 1; b >= 0; --b) f = (f << 2) | (uint32_t)((((by >> b) & 1) << 1) | ((bx >> b) & 1));
     return (f << g.fine_z_bits) | (uint32_t)bz;
 }
 
+// known_b >= 0: the batch entry of the point is already known (a radix tile that lies inside one point set)
 __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, const BatchRef& batch,
-                                              long long i, const Geom& g, const KeyFast& f) {
-    long long b = batch_of(batch, i);
+                                              long long i, const Geom& g, const KeyFast& f, long long known_b = -1) {
+    long long b = known_b >= 0 ? known_b : batch_of(batch, i);
     b = b < 0 ? 0 : (b >= g.B ? g.B - 1 : b);
     uint32_t key = (uint32_t)b;
     const float Mf = (float)g.M;
@@ -302,15 +304,23 @@ key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n
                 uint32_t* __restrict__ keys, uint32_t* __restrict__ table, int nblocks,
                 uint32_t* __restrict__ sample_counts = nullptr, int sample_mask = 0) {
     __shared__ uint32_t hist[kRsBins];
+    __shared__ long long s_b[2];
     hist[threadIdx.x] = 0;
+    const long long base = (long long)blockIdx.x * kRsTile;
+    // offsets: the point sets are contiguous, so almost every radix tile lies inside ONE of them -- look the batch
+    // entry up once per tile instead of with a binary search per point
+    if (threadIdx.x < 2 && batch.data && batch.offsets) {
+        const long long last = base + kRsTile - 1 < n ? base + kRsTile - 1 : n - 1;
+        s_b[threadIdx.x] = batch_of(batch, threadIdx.x == 0 ? base : last);
+    }
     __syncthreads();
     const KeyFast f = key_fast(g);
-    const long long base = (long long)blockIdx.x * kRsTile;
+    const long long tile_b = (batch.data && batch.offsets && s_b[0] == s_b[1]) ? s_b[0] : -1;
 #pragma unroll 4
     for (int k = 0; k < kRsIpt; ++k) {
         const long long i = base + (long long)k * kRsThreads + threadIdx.x;
         if (i < n) {
-            const uint32_t key = point_key(pos, batch, i, g, f);
+            const uint32_t key = point_key(pos, batch, i, g, f, tile_b);
             keys[i] = key;
             atomicAdd(&hist[key & 255u], 1u);
             // Geom::mixed: every (sample_mask + 1)-th point is counted into its tile (see density_flag_kernel)
