@@ -270,6 +270,23 @@ count_sorted_kernel(const uint32_t* __restrict__ keys_sorted, long long n, int f
     }
 }
 
+// The same from a binary search per bin: bin_start[b] = first sorted position whose tile key is >= b (b = 0 .. nbins).
+// 24 dependent loads per bin instead of a pass over all keys plus a scan: used when there are far fewer bins than
+// points (c4: 16 384 bins, 2^24 points -- 12 us instead of 56 + 15 us).
+__global__ void __launch_bounds__(256)
+bin_search_kernel(const uint32_t* __restrict__ keys_sorted, long long n, int fine_bits, long long nbins,
+                  uint32_t* __restrict__ bin_start) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nbins) return;
+    long long lo = 0, hi = n;  // first position in [0, n] with key >= b
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((long long)(__ldg(keys_sorted + mid) >> fine_bits) < b) lo = mid + 1;
+        else hi = mid;
+    }
+    bin_start[b] = (uint32_t)lo;
+}
+
 // ------------------------------------------------------------------------- stable radix sort
 #ifndef NFFT_SORT_MINB
 #define NFFT_SORT_MINB 5  // resident CTAs per SM the scatter kernel is compiled for (register cap)
@@ -619,9 +636,12 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
     // either its output or, if it did not run, the unsorted keys with the identity payload.  A uniform point set
     // pays the sampling and a few empty launches, not the pass (0.2 ms at 2^24 points).
     const bool refine = g.mixed && g.refine_pass && passes >= 2 && n > 0;
+    // bin offsets by binary search in the sorted keys when there are far fewer bins than points
+    const bool search_bins = passes > 0 && !single_pass && nbins * 8 <= n;
     if (!single_pass) {
-        // bin_count (and, right behind it, the sample counts in nch) = 0
-        NF_CUDA(cudaMemsetAsync(bin_count, 0, (refine ? L.nch - L.bin_count : 0) + (size_t)(nbins + 1) * 4, st));
+        // bin_count = 0 (unless the offsets come from the search), the sample counts in nch = 0 (refine)
+        if (!search_bins) NF_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, st));
+        if (refine) NF_CUDA(cudaMemsetAsync(nch, 0, (size_t)(nbins + 1) * 4, st));
         NF_CUDA(cudaMemsetAsync(plan->flags, 0, kPlanFlagWords * 4, st));
     }
     // stable LSD radix sort of (key, index) over the key bits that can be set
@@ -659,12 +679,14 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
                       g.pmax, bin_start, chunk_start, plan->items, plan->max_items, plan->flags);
             return NFFTB200_OK;
         }
-        if (passes > 0) {
+        if (search_bins) {
+            NF_LAUNCH(bin_search_kernel, (unsigned)((nbins + 256) / 256), 256, 0, st, kin, n, g.fine_bits, nbins, bin_start);
+        } else if (passes > 0) {
             NF_LAUNCH(count_sorted_kernel, (unsigned)((n + 255) / 256), 256, 0, st, kin, n, g.fine_bits, bin_count);
         }
     }
     // bin offsets, chunks of at most pmax points, work items
-    NF_TRY(scan_exclusive(bin_count, bin_start, nbins, scan, st));
+    if (!search_bins) NF_TRY(scan_exclusive(bin_count, bin_start, nbins, scan, st));
     NF_LAUNCH(chunk_count_kernel, (unsigned)((nbins + 255) / 256), 256, 0, st, bin_start, nbins, g.pmax, nch);
     NF_TRY(scan_exclusive(nch, chunk_start, nbins, scan, st));
     NF_CUDA(cudaMemsetAsync(plan->items, 0, (size_t)plan->max_items * sizeof(uint4), st));
