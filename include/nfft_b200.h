@@ -115,7 +115,9 @@ size_t nfftb200_plan_bytes(int64_t n, int64_t n_geom, int d, int64_t N, int m, i
 int nfftb200_plan_points(const float* pos, const int64_t* batch, void* plan, size_t plan_bytes,
                          int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B, int64_t C,
                          int flags, void* workspace, size_t workspace_bytes, void* stream);
-/* flags_out[8] on the HOST; flags_out[0] = points found outside their tile so far.  Synchronises. */
+/* flags_out[8] on the HOST; flags_out[0] = points found outside their tile so far, [1] = TMA tile loads that did
+ * not complete (must be 0), [2] = 1 if the binning (with NFFTB200_CLUSTERED) found the point set clustered and marked
+ * its heavy tiles for the 2 x 2 x 2 sweep.  Synchronises. */
 int nfftb200_plan_flags(const void* plan, int64_t n, int64_t n_geom, int d, int64_t N, int m, int64_t B,
                         int64_t C, int flags, uint32_t* flags_out, void* stream);
 
