@@ -64,6 +64,36 @@ def test_geometry_query():
     assert g["spread_threads"] >= g["L"] ** 2
 
 
+def test_clustered_hint_changes_only_the_binning_geometry():
+    """NFFTB200_CLUSTERED (NfftPlan(clustered=True)) enables the per-tile density decision for large 3D sets with
+    cutoff 3 or 4: the keys carry the 2 x 2 x 2 hierarchy, left-aligned so that the lowest radix pass is fine bits
+    only; everything else of the tiling is unchanged.  Host-only query."""
+    plain = _lib.geometry(3, 128, 4, 4, 1, 0, 2 ** 24)
+    hinted = _lib.geometry(3, 128, 4, 4, 1, _lib.CLUSTERED, 2 ** 24)
+    assert plain["mixed"] == 0 and (plain["scx"], plain["scy"], plain["scz"], plain["fine_bits"]) == (4, 4, 2, 2)
+    assert hinted["mixed"] == 1 and hinted["refine_pass"] == 1 and hinted["dense_tile_pts"] == 2048
+    assert (hinted["scx"], hinted["scy"], hinted["scz"], hinted["fine_bits"]) == (2, 2, 2, 10)  # 14 tile bits + 10 = 3 passes
+    for k in ("M", "Tx", "Ty", "Tz", "ntx", "Px", "Py", "Pz", "sY", "sZ", "tile_elems", "pmax", "use_reg"):
+        assert plain[k] == hinted[k]
+    # small point sets, other cutoffs, 2D and dense sets ignore the hint
+    assert _lib.geometry(3, 128, 4, 4, 1, _lib.CLUSTERED, 1000)["mixed"] == 0
+    assert _lib.geometry(3, 128, 2, 4, 1, _lib.CLUSTERED, 2 ** 24)["mixed"] == 0
+    assert _lib.geometry(2, 256, 4, 16, 8, _lib.CLUSTERED, 2 ** 23)["mixed"] == 0
+    dense = _lib.geometry(3, 64, 4, 1, 1, _lib.CLUSTERED, 2 ** 26)
+    assert dense["mixed"] == 0 and (dense["scx"], dense["scy"], dense["scz"]) == (2, 2, 2)
+    # the test hook switches the mode for every call and lowers the size threshold
+    L = _lib.lib()
+    try:
+        L.nfftb200_debug_mixed(1, 0, 600)
+        forced = _lib.geometry(3, 32, 4, 2, 1, 0, 30000)
+        assert forced["mixed"] == 1 and forced["dense_tile_pts"] == 600 and forced["fine_bits"] == 9
+        L.nfftb200_debug_mixed(0, 0, 0)
+        assert _lib.geometry(3, 128, 4, 4, 1, _lib.CLUSTERED, 2 ** 24)["mixed"] == 0
+    finally:
+        L.nfftb200_debug_mixed(-1, -1, 0)
+    assert _lib.geometry(3, 128, 4, 4, 1, _lib.CLUSTERED, 2 ** 24)["mixed"] == 1
+
+
 def test_cpu_tensors_raise_like_the_reference():
     """reference csrc/core.cpp:52 asserts x.device().is_cuda(); so do we -- no CPU fallback."""
     pos = torch.rand(10, 2) - 0.5
