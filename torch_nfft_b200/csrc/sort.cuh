@@ -166,14 +166,18 @@ __device__ __forceinline__ int wrap_mod(int v, int M) {
 // division cost ~25 instructions each, six per point.
 struct KeyFast {
     bool m_pow2;
-    int tshift[3];  // log2(T[slot]) or -1
+    int tshift[3];    // log2(T[slot]) or -1
+    int sc_shift[3];  // log2(sc[slot]) (supercell extents are powers of two whenever fine key bits are used)
 };
 
 __device__ __forceinline__ KeyFast key_fast(const Geom& g) {
     KeyFast f;
     f.m_pow2 = (g.M & (g.M - 1)) == 0;
 #pragma unroll
-    for (int s = 0; s < 3; ++s) f.tshift[s] = (g.T[s] & (g.T[s] - 1)) == 0 ? __ffs(g.T[s]) - 1 : -1;
+    for (int s = 0; s < 3; ++s) {
+        f.tshift[s] = (g.T[s] & (g.T[s] - 1)) == 0 ? __ffs(g.T[s]) - 1 : -1;
+        f.sc_shift[s] = __ffs(g.sc[s]) - 1;
+    }
     return f;
 }
 
@@ -203,9 +207,9 @@ __device__ __forceinline__ long long batch_of(const BatchRef& br, long long i) {
 // (tile, fine) makes the chunks a heavy tile is cut into spatially compact -- a quadrant, a supercell column,
 // a z-range of it -- instead of random samples of the whole tile, so the points of a chunk share register
 // blocks in the sweep (window_reg.cuh).
-__device__ __forceinline__ uint32_t fine_index(int cx, int cy, int cz, const Geom& g) {
+__device__ __forceinline__ uint32_t fine_index(int cx, int cy, int cz, const Geom& g, const KeyFast& kf) {
     // supercell extents are powers of two whenever fine bits are used (make_geom): shifts, not divisions
-    const int bx = cx >> (__ffs(g.sc[0]) - 1), by = cy >> (__ffs(g.sc[1]) - 1), bz = cz >> (__ffs(g.sc[2]) - 1);
+    const int bx = cx >> kf.sc_shift[0], by = cy >> kf.sc_shift[1], bz = cz >> kf.sc_shift[2];
     uint32_t f = 0;
     for (int b = g.fine_xy_levels - 1; b >= 0; --b) f = (f << 2) | (uint32_t)((((by >> b) & 1) << 1) | ((bx >> b) & 1));
     return (f << g.fine_z_bits) | (uint32_t)bz;
@@ -233,7 +237,42 @@ __device__ __forceinline__ uint32_t point_key(const float* __restrict__ pos, con
     if (g.fine_bits > 0) {
         // the top fine_bits bits of the hierarchical index (Geom::mixed: left-aligned in a field that may be wider)
         const int total = 2 * g.fine_xy_levels + g.fine_z_bits;
-        const uint32_t fi = fine_index(in_tile[0], in_tile[1], in_tile[2], g);
+        const uint32_t fi = fine_index(in_tile[0], in_tile[1], in_tile[2], g, f);
+        key = (key << g.fine_bits) | (g.fine_bits >= total ? fi << (g.fine_bits - total) : fi >> (total - g.fine_bits));
+    }
+    return key;
+}
+
+// The same key with the dimension and "M and the tile edges are powers of two" known at compile time: no runtime
+// dimension tests, no integer divisions (ncu of the generic version at c4: 173 instructions per point, issue
+// slots 81 % busy -- the key kernel was instruction-bound, profiles/r03c_misc_kernels.txt).
+template <int DIM, bool POW2>
+__device__ __forceinline__ uint32_t point_key_t(const float* __restrict__ pos, const BatchRef& batch, long long i,
+                                                const Geom& g, const KeyFast& f, long long known_b) {
+    long long b = known_b >= 0 ? known_b : batch_of(batch, i);
+    b = b < 0 ? 0 : (b >= g.B ? g.B - 1 : b);
+    uint32_t key = (uint32_t)b;
+    const float Mf = (float)g.M;
+    const float* p = pos + i * DIM;
+    int in_tile[3] = {0, 0, 0};
+#pragma unroll
+    for (int slot = DIM - 1; slot >= 0; --slot) {
+        const int c = (int)floorf(p[DIM - 1 - slot] * Mf);  // spatial_window_operations.cu:50
+        int tile;
+        if (POW2) {
+            const int cw = c & (g.M - 1);
+            tile = cw >> f.tshift[slot];
+            in_tile[slot] = cw & (g.T[slot] - 1);
+        } else {
+            const int cw = f.m_pow2 ? (c & (g.M - 1)) : wrap_mod(c, g.M);
+            tile = f.tshift[slot] >= 0 ? (cw >> f.tshift[slot]) : cw / g.T[slot];
+            in_tile[slot] = cw - tile * g.T[slot];
+        }
+        key = key * (uint32_t)g.nt[slot] + (uint32_t)tile;
+    }
+    if (g.fine_bits > 0) {
+        const int total = 2 * g.fine_xy_levels + g.fine_z_bits;
+        const uint32_t fi = fine_index(in_tile[0], in_tile[1], in_tile[2], g, f);
         key = (key << g.fine_bits) | (g.fine_bits >= total ? fi << (g.fine_bits - total) : fi >> (total - g.fine_bits));
     }
     return key;
@@ -316,6 +355,7 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uin
 
 // Keys of one radix tile and, in the same pass, the tile's row of the first radix pass's digit table
 // (saves re-reading the keys in radix_hist_kernel).
+template <int DIM, bool POW2>
 __global__ void __launch_bounds__(kRsThreads)
 key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n, Geom g,
                 uint32_t* __restrict__ keys, uint32_t* __restrict__ table, int nblocks,
@@ -337,7 +377,7 @@ key_tile_kernel(const float* __restrict__ pos, const BatchRef batch, long long n
     for (int k = 0; k < kRsIpt; ++k) {
         const long long i = base + (long long)k * kRsThreads + threadIdx.x;
         if (i < n) {
-            const uint32_t key = point_key(pos, batch, i, g, f, tile_b);
+            const uint32_t key = point_key_t<DIM, POW2>(pos, batch, i, g, f, tile_b);
             keys[i] = key;
             atomicAdd(&hist[key & 255u], 1u);
             // Geom::mixed: every (sample_mask + 1)-th point is counted into its tile (see density_flag_kernel)
@@ -652,8 +692,15 @@ inline int sort_points(const float* pos, const int64_t* batch, bool batch_is_off
             NF_LAUNCH(key_hist_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pos, bref, n, g, keys0, bin_count);
             NF_LAUNCH(iota_kernel, (unsigned)((n + 255) / 256), 256, 0, st, plan->perm, n);
         } else {
-            NF_LAUNCH(key_tile_kernel, (unsigned)L.nblocks, kRsThreads, 0, st, pos, bref, n, g, keys0, table,
-                      (int)L.nblocks, refine ? nch : nullptr, sample_stride - 1);
+            bool pow2 = (g.M & (g.M - 1)) == 0;
+            for (int sl = 0; sl < g.dim; ++sl) pow2 = pow2 && (g.T[sl] & (g.T[sl] - 1)) == 0;
+#define NF_KEY_TILE(D_, P_)                                                                                    \
+            NF_LAUNCH((key_tile_kernel<D_, P_>), (unsigned)L.nblocks, kRsThreads, 0, st, pos, bref, n, g, keys0, \
+                      table, (int)L.nblocks, refine ? nch : nullptr, sample_stride - 1)
+            if (g.dim == 1) { if (pow2) NF_KEY_TILE(1, true); else NF_KEY_TILE(1, false); }
+            else if (g.dim == 2) { if (pow2) NF_KEY_TILE(2, true); else NF_KEY_TILE(2, false); }
+            else { if (pow2) NF_KEY_TILE(3, true); else NF_KEY_TILE(3, false); }
+#undef NF_KEY_TILE
         }
         uint32_t* refined = plan->flags + 2;
         if (refine)

@@ -37,13 +37,28 @@ unpack_kernel(const float2* __restrict__ spec, float* __restrict__ y, Geom g) {
     for (int a = 0; a < DIM; ++a) nd *= g.N;
     const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total * nd) return;
-    const int c = (int)(idx % g.C);
-    I f = idx / g.C;
+    // index decode: shifts when N and C are powers of two (the kernel is instruction-bound otherwise: five integer
+    // divisions per output, ncu: issue slots 79 % busy, profiles/r03c_misc_kernels.txt)
+    int c;
+    I f;
     int k[3] = {0, 0, 0};
+    if (((g.N & (g.N - 1)) | (g.C & (g.C - 1))) == 0) {
+        const int cs = __ffs(g.C) - 1, ns = __ffs(g.N) - 1;
+        c = (int)(idx & (I)(g.C - 1));
+        f = idx >> cs;
 #pragma unroll
-    for (int a = DIM - 1; a >= 0; --a) {
-        k[a] = (int)(f % g.N) - g.N / 2;
-        f /= g.N;
+        for (int a = DIM - 1; a >= 0; --a) {
+            k[a] = (int)(f & (I)(g.N - 1)) - g.N / 2;
+            f >>= ns;
+        }
+    } else {
+        c = (int)(idx % g.C);
+        f = idx / g.C;
+#pragma unroll
+        for (int a = DIM - 1; a >= 0; --a) {
+            k[a] = (int)(f % g.N) - g.N / 2;
+            f /= g.N;
+        }
     }
     const I bc = f * g.C + c;
     float factor = 1.0f;
