@@ -16,6 +16,8 @@
 //   stage A: thread <-> x2, a 16-point DFT over x1 in registers, twiddle, transposed through shared memory
 //   stage B: thread <-> k1, an R2-point DFT over x2 in registers; only k2 <= R2/4 is kept (k <= M/4)
 // and the inverse runs the same two stages in the opposite order with conjugated twiddles.
+// tests/test_fft_rows_model.py restates these index maps in numpy (CPU); the kernels themselves are compared with
+// the cuFFT path in tests/test_parity_gpu.py::test_pruned_fft_matches_cufft_path.
 #pragma once
 #include "common.cuh"
 
